@@ -1,0 +1,104 @@
+/*
+ * dirt_b200.h -- C ABI of libdirt_b200.so, the sm_100a replacement for the
+ * `Rasterise` / `RasteriseGrad` custom ops of pmh47/dirt.
+ *
+ * Every entry point takes plain device pointers and sizes (no torch / TF types),
+ * enqueues all its work on the CUDA stream it is given, never synchronises the
+ * host, never allocates device memory and keeps no global state.  The caller
+ * owns every buffer, including the workspace.
+ *
+ * Reference interfaces replaced (paths relative to the reference checkout):
+ *   dirt_rasterise_forward   <- REGISTER_OP("Rasterise") + RasteriseOpGpu::Compute
+ *                               csrc/rasterise_egl.cpp:32-51, 276-408
+ *   dirt_rasterise_backward  <- REGISTER_OP("RasteriseGrad") + RasteriseGradOpGpu::Compute
+ *                               csrc/rasterise_grad_egl.cpp:33-53, 324-485 and the kernel
+ *                               assemble_grads, csrc/rasterise_grad_egl.cu:93-236
+ *   dirt_rasterise_visibility<- the backward G-buffer (barycentrics, clip-w, indices) that
+ *                               the reference renders with GL, csrc/shaders.cpp:45-79,
+ *                               csrc/rasterise_grad_egl.cpp:432-456 (debug / parity tests)
+ *   height/width/channels    <- the HWC op attributes, csrc/hwc.h:7-30
+ *
+ * Layouts (all row-major, channels last, row 0 = top of the image = clip-space y=+1,
+ * csrc/rasterise_egl.cu:23,80):
+ *   background, pixels, grad_pixels, grad_background : float32 [B, H, W, C]
+ *   vertices, grad_vertices                          : float32 [B, V, 4]   (clip space x,y,z,w)
+ *   vertex_colors, grad_vertex_colors                : float32 [B, V, C]
+ *   faces                                            : int32   [B, F, 3]
+ *   face_ids                                         : int32   [B, H, W]   (-1 = background)
+ *   gbuffer                                          : float32 [B, H, W, 4] (bary0, bary1, bary2, clip_w;
+ *                                                      (-1,-1,-1,+inf) where uncovered)
+ */
+#ifndef DIRT_B200_H
+#define DIRT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Error codes: 0 on success, negative on failure.  Nothing aborts the process
+ * (the reference LOG(FATAL)s on every CUDA/GL error, csrc/rasterise_egl.cpp:82-86). */
+enum {
+    DIRT_OK = 0,
+    DIRT_ERR_BAD_SHAPE = -1,        /* B,H,W,C,V,F out of range (csrc/hwc.h:27-28; rasterise_egl.cpp:301-316) */
+    DIRT_ERR_NULL_POINTER = -2,
+    DIRT_ERR_WORKSPACE_TOO_SMALL = -3,
+    DIRT_ERR_BAD_CHANNEL_GROUPS = -4, /* groups must be 1 or 3 wide and sum to C (rasterise_ops.py:80-108) */
+    DIRT_ERR_TOO_MANY_VERTICES = -5,  /* V > 2^24, csrc/rasterise_grad_egl.cpp:399-405 */
+    DIRT_ERR_CUDA = -6,               /* a CUDA runtime call or kernel launch failed */
+    DIRT_ERR_MISALIGNED = -7          /* a pointer is not aligned as required (workspace: 256 B, tensors: 4 B) */
+};
+
+/* Human-readable text for an error code (static storage, never NULL). */
+const char* dirt_error_string(int code);
+
+/* Library / ABI version, bumped whenever a signature changes. */
+int dirt_abi_version(void);
+
+/* Bytes of device workspace that forward / backward / visibility need for these sizes.
+ * Deterministic function of the sizes only (no data dependence, no host sync):
+ * triangle records + bounded per-tile reference lists + per-tile counters. */
+size_t dirt_workspace_bytes(int B, int H, int W, int C, int V, int F);
+
+/* Forward: pixels = rasterise(background, vertices, vertex_colors, faces).
+ * Handles any C >= 1 in one pass (the reference runs one op per channel group of 3 or 1,
+ * rasterise_ops.py:86-108; the forward result does not depend on the grouping).
+ * face_ids_out may be NULL; when given it receives the per-pixel visible face index,
+ * which dirt_rasterise_backward accepts back to skip re-deriving visibility. */
+int dirt_rasterise_forward(const float* background, const float* vertices,
+                           const float* vertex_colors, const int32_t* faces,
+                           float* pixels, int32_t* face_ids_out,
+                           int B, int H, int W, int C, int V, int F,
+                           void* workspace, size_t workspace_bytes, void* cuda_stream);
+
+/* Backward: the RasteriseGrad op.  `pixels` is an input (deferred shading passes shaded
+ * pixels, rasterise_ops.py:206-210).  channel_groups (host pointer) lists the widths of the
+ * reference's channel groups, e.g. {3,1} for C=4; each group takes its own Scharr / dilation
+ * decision and grad_vertices is summed over groups (rasterise_ops.py:163).  NULL/0 means the
+ * reference's own greedy split of C.
+ * face_ids may be NULL: visibility is then re-derived from (vertices, faces) inside the call.
+ * grad_vertices / grad_vertex_colors are zeroed by the library before accumulation;
+ * grad_background is written exactly once per pixel. */
+int dirt_rasterise_backward(const float* vertices, const int32_t* faces,
+                            const float* pixels, const float* grad_pixels,
+                            const int32_t* face_ids,
+                            float* grad_background, float* grad_vertices, float* grad_vertex_colors,
+                            int B, int H, int W, int C, int V, int F,
+                            const int* channel_groups, int n_groups,
+                            void* workspace, size_t workspace_bytes, void* cuda_stream);
+
+/* Debug / parity: the visibility G-buffer alone (either output may be NULL). */
+int dirt_rasterise_visibility(const float* vertices, const int32_t* faces,
+                              int32_t* face_ids, float* gbuffer,
+                              int B, int H, int W, int V, int F,
+                              void* workspace, size_t workspace_bytes, void* cuda_stream);
+
+/* Number of kernels the last call on this thread launched (bench.py's gpu_launches). */
+int dirt_last_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DIRT_B200_H */
