@@ -1,0 +1,458 @@
+#!/usr/bin/env python
+"""bench.py -- fwd+bwd Mpixels/s of the rasterise hot path on BASELINE.json's workload.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg3|cfg4|cfg5|cfg2]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" is one forward + one backward pass of the hot path over one batch of synthetic scenes
+(BASELINE cfg3 by default: batch 64 per GPU, 512x512, 4-channel G-buffer, 5120-triangle icosphere with a
+pose per item), called through the C ABI of libdirt_b200.so with every buffer already resident in HBM,
+followed by the batch reduction of the vertex gradients and -- when N > 1 -- ONE NCCL all-reduce of that
+[V, 4+C] buffer (the batch shards over GPUs with no other exchange: weak scaling, 64 images per GPU).
+
+One JSON line on rank 0:  value = B_total*H*W / step time (CUDA events, max over ranks);  e2e = the same
+call with HOST (pinned) buffers, host<->device copies inside the timed region;  roofline = the dominant
+kernel against the measured HBM copy peak;  cpu_baseline = the CPU oracle on a bounded sample.
+--impl reference times the CPU port of the reference path (oracle/), the only runnable reference here.
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = 'fwd+bwd Mpixels/sec'
+UNIT = 'Mpixels/s'
+
+WORKLOADS = {
+    # name: (generator, kwargs, description)
+    'cfg3': ('config3', dict(batch=64, width=512, height=512), 'BASELINE cfg3: batch=64/GPU, 512x512, 4-channel G-buffer, icosphere-4 (V=2562, F=5120), per-item pose'),
+    'cfg4': ('config4', dict(batch=32, width=512, height=512), 'BASELINE cfg4 shard: batch=32/GPU, 512x512, 3-channel, icosphere-4'),
+    'cfg5': ('config5', dict(batch=64, width=1024, height=1024), 'BASELINE cfg5: batch=64/GPU, 1024x1024, 3-channel, UV sphere (V=24866, F=49728)'),
+    'cfg2': ('config2', dict(), 'BASELINE cfg2: batch=1, 256x256, 3-channel, icosphere-3'),
+}
+
+
+def algorithmic_bytes(B, H, W, C, V, F):
+    """per image fwd = 2*H*W*C*4 + V*16 + V*C*4 + F*12; bwd = 3*H*W*C*4 + V*16 + F*12 + V*16 + V*C*4."""
+    fwd = B * (2 * H * W * C * 4 + V * 16 + V * C * 4 + F * 12)
+    bwd = B * (3 * H * W * C * 4 + V * 16 + F * 12 + V * 16 + V * C * 4)
+    return fwd, bwd
+
+
+def measured_peak_gbs():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    try:
+        with open(path) as f:
+            return float(json.load(f)['hbm_gbs']), 'measured (MEASURED_PEAKS.json hbm_gbs, burst copy)'
+    except Exception:
+        return 6650.0, 'fallback (B200_PROFILING.md: 6.65 TB/s)'
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clocks and throttle reasons with nvidia-smi while the timed region runs."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.stop_flag = threading.Event()
+        self.samples = []
+        self.proc = None
+
+    def run(self):
+        q = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+             'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + q,
+                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                self.samples.append(line.strip())
+                if self.stop_flag.is_set():
+                    break
+        except Exception:
+            pass
+
+    def finish(self):
+        self.stop_flag.set()
+        if self.proc is not None:
+            try:
+                self.proc.terminate()
+            except Exception:
+                pass
+        sm, smax, reasons = [], [], set()
+        for line in self.samples:
+            parts = [p.strip() for p in line.split(',')]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0])); smax.append(float(parts[1]))
+            except ValueError:
+                continue
+            for name, val in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), parts[2:6]):
+                if val.lower().startswith('active'):
+                    reasons.add(name)
+        if not sm:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': [], 'samples': 0}
+        return {'sm_mhz': float(np.median(sm)), 'sm_max_mhz': float(max(smax)), 'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------------------
+
+class PreparedStep:
+    """Preallocated buffers + the two C-ABI calls of one step (forward, backward with cached visibility)."""
+
+    def __init__(self, scene, device, grad_seed=2):
+        import torch
+        from dirt_b200 import _lib
+        self.torch = torch
+        self.lib = _lib.lib()
+        self._check = _lib.check
+        self.device = device
+        self.host = scene
+        B, H, W, C = scene['background'].shape
+        V, F = scene['vertices'].shape[1], scene['faces'].shape[1]
+        self.dims = (B, H, W, C, V, F)
+        self.grad_pixels_host = np.random.default_rng(grad_seed).standard_normal((B, H, W, C)).astype(np.float32)
+        dev = {k: torch.from_numpy(v).to(device) for k, v in scene.items()}
+        self.background, self.vertices = dev['background'], dev['vertices']
+        self.vertex_colors, self.faces = dev['vertex_colors'], dev['faces']
+        self.grad_pixels = torch.from_numpy(self.grad_pixels_host).to(device)
+        self.pixels = torch.empty_like(self.background)
+        self.face_ids = torch.empty((B, H, W), dtype=torch.int32, device=device)
+        self.grad_background = torch.empty_like(self.background)
+        self.grad_vertices = torch.empty((B, V, 4), dtype=torch.float32, device=device)
+        self.grad_vertex_colors = torch.empty((B, V, C), dtype=torch.float32, device=device)
+        self.shared_grad = torch.empty((V, 4 + C), dtype=torch.float32, device=device)
+        self.ws_bytes = int(self.lib.dirt_workspace_bytes(B, H, W, C, V, F))
+        self.workspace = torch.empty(self.ws_bytes, dtype=torch.uint8, device=device)
+        self.launches_per_step = 0
+
+    def _p(self, t):
+        return ctypes.c_void_p(t.data_ptr())
+
+    def forward(self):
+        B, H, W, C, V, F = self.dims
+        stream = ctypes.c_void_p(self.torch.cuda.current_stream(self.device).cuda_stream)
+        rc = self.lib.dirt_rasterise_forward(self._p(self.background), self._p(self.vertices), self._p(self.vertex_colors),
+                                             self._p(self.faces), self._p(self.pixels), self._p(self.face_ids), B, H, W, C, V, F,
+                                             self._p(self.workspace), self.ws_bytes, stream)
+        self._check(rc, 'Rasterise')
+        return self.lib.dirt_last_launch_count()
+
+    def backward(self):
+        B, H, W, C, V, F = self.dims
+        stream = ctypes.c_void_p(self.torch.cuda.current_stream(self.device).cuda_stream)
+        rc = self.lib.dirt_rasterise_backward(self._p(self.vertices), self._p(self.faces), self._p(self.pixels),
+                                              self._p(self.grad_pixels), self._p(self.face_ids), self._p(self.grad_background),
+                                              self._p(self.grad_vertices), self._p(self.grad_vertex_colors), B, H, W, C, V, F,
+                                              None, 0, self._p(self.workspace), self.ws_bytes, stream)
+        self._check(rc, 'RasteriseGrad')
+        return self.lib.dirt_last_launch_count()
+
+    def step(self, world):
+        n = self.forward()
+        n += self.backward()
+        # shared-geometry reduction: sum the per-item vertex gradients of this shard, all-reduce across GPUs
+        self.torch.sum(self.grad_vertices, dim=0, out=self.shared_grad[:, :4])
+        self.torch.sum(self.grad_vertex_colors, dim=0, out=self.shared_grad[:, 4:])
+        if world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(self.shared_grad, op=dist.ReduceOp.SUM)
+        self.launches_per_step = n
+        return n
+
+
+class HostStep:
+    """The same two calls with HOST buffers: pinned inputs -> device, run, outputs -> pinned host."""
+
+    def __init__(self, prepared):
+        torch = prepared.torch
+        self.p = prepared
+        self.torch = torch
+        pin = lambda a: torch.from_numpy(a).pin_memory()
+        s = prepared.host
+        self.h_in = dict(background=pin(s['background']), vertices=pin(s['vertices']), vertex_colors=pin(s['vertex_colors']),
+                         faces=pin(s['faces']), grad_pixels=pin(prepared.grad_pixels_host))
+        self.h_out = {k: torch.empty(getattr(prepared, k).shape, dtype=getattr(prepared, k).dtype).pin_memory()
+                      for k in ('pixels', 'grad_background', 'grad_vertices', 'grad_vertex_colors')}
+        self.h2d = sum(t.numel() * t.element_size() for t in self.h_in.values())
+        self.d2h = sum(t.numel() * t.element_size() for t in self.h_out.values())
+
+    def step(self):
+        p = self.p
+        p.background.copy_(self.h_in['background'], non_blocking=True)
+        p.vertices.copy_(self.h_in['vertices'], non_blocking=True)
+        p.vertex_colors.copy_(self.h_in['vertex_colors'], non_blocking=True)
+        p.faces.copy_(self.h_in['faces'], non_blocking=True)
+        p.forward()
+        self.h_out['pixels'].copy_(p.pixels, non_blocking=True)
+        p.grad_pixels.copy_(self.h_in['grad_pixels'], non_blocking=True)
+        p.backward()
+        self.h_out['grad_background'].copy_(p.grad_background, non_blocking=True)
+        self.h_out['grad_vertices'].copy_(p.grad_vertices, non_blocking=True)
+        self.h_out['grad_vertex_colors'].copy_(p.grad_vertex_colors, non_blocking=True)
+
+
+def cpu_baseline(scene, grad_pixels, sample_images, threads=None):
+    """fwd+bwd of the CPU oracle (a port of the reference path) on `sample_images` images of the workload."""
+    from oracle import oracle
+    if threads:
+        oracle.set_threads(threads)
+    n = min(sample_images, scene['background'].shape[0])
+    sub = {k: np.ascontiguousarray(v[:n]) for k, v in scene.items()}
+    gp = np.ascontiguousarray(grad_pixels[:n])
+    t0 = time.perf_counter()
+    pixels = oracle.forward(**sub)
+    oracle.backward(sub['vertices'], sub['faces'], pixels, gp)
+    dt = time.perf_counter() - t0
+    H, W = scene['background'].shape[1:3]
+    return n * H * W / dt / 1e6, n, dt, oracle.threads()
+
+
+def run_ours(args):
+    import torch
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    if not torch.cuda.is_available():
+        raise RuntimeError('bench.py needs a CUDA device (there is no CPU fallback for the product path)')
+    torch.cuda.set_device(local_rank)
+    device = torch.device('cuda', local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group('nccl', device_id=device)
+    from dirt_b200 import build as lib_build, scenes
+    if rank == 0:
+        lib_build.build()
+    if world > 1:
+        dist.barrier()
+
+    gen, kwargs, desc = WORKLOADS[args.workload]
+    kwargs = dict(kwargs)
+    if args.batch:
+        kwargs['batch'] = args.batch
+    if 'seed' not in kwargs and args.workload != 'cfg2':
+        kwargs['seed'] = 1 + rank  # every rank renders different poses
+    scene = getattr(scenes, gen)(**kwargs)
+    prep = PreparedStep(scene, device)
+    B, H, W, C, V, F = prep.dims
+
+    def sync_all():
+        torch.cuda.synchronize(device)
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize(device)
+
+    for _ in range(max(args.warmup, 3)):
+        prep.step(world)
+    sync_all()
+
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+        time.sleep(0.25)
+    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sync_all()
+    start.record()
+    launches = 0
+    for _ in range(args.steps):
+        launches += prep.step(world)
+    stop.record()
+    sync_all()
+    elapsed_ms = start.elapsed_time(stop)
+    # keep the GPU busy a little longer so the clock sampler sees the loaded state even for short runs
+    if sampler:
+        t_end = time.time() + 0.6
+        while time.time() < t_end:
+            prep.step(world)
+        torch.cuda.synchronize(device)
+    clocks = sampler.finish() if sampler else None
+    t = torch.tensor([elapsed_ms], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    elapsed_ms = float(t.item())
+    ms_per_step = elapsed_ms / args.steps
+    value = world * B * H * W / (ms_per_step * 1e-3) / 1e6
+
+    # per-phase and per-kernel timings (separate loops, same buffers; inputs exceed L2 so no flush is needed)
+    def time_phase(fn, n):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize(device)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        torch.cuda.synchronize(device)
+        return e0.elapsed_time(e1) / n
+
+    n_phase = max(3, min(args.steps, 20))
+    fwd_ms = time_phase(prep.forward, n_phase)
+    bwd_ms = time_phase(prep.backward, n_phase)
+
+    def time_kernel(which, fn, n):
+        prep.lib.dirt_kernel_timer_enable(which)
+        total = 0.0
+        for _ in range(n):
+            fn()
+            total += float(prep.lib.dirt_kernel_timer_elapsed_ms())
+        prep.lib.dirt_kernel_timer_enable(0)
+        return total / n
+
+    k_fwd_ms = time_kernel(1, prep.forward, n_phase)
+    k_bwd_ms = time_kernel(2, prep.backward, n_phase)
+
+    # end to end with host buffers
+    e2e = None
+    if not args.no_e2e:
+        host = HostStep(prep)
+        for _ in range(2):
+            host.step()
+        sync_all()
+        n_e2e = max(2, min(args.steps, 5))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n_e2e):
+            host.step()
+        e1.record()
+        sync_all()
+        te = torch.tensor([e0.elapsed_time(e1) / n_e2e], dtype=torch.float64, device=device)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e2e_ms = float(te.item())
+        e2e = {'value': world * B * H * W / (e2e_ms * 1e-3) / 1e6, 'unit': UNIT, 'ms_per_step': e2e_ms,
+               'h2d_bytes_per_step': int(host.h2d), 'd2h_bytes_per_step': int(host.d2h)}
+        del host
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peak, peak_src = measured_peak_gbs()
+    fwd_bytes, bwd_bytes = algorithmic_bytes(B, H, W, C, V, F)
+    if k_bwd_ms >= k_fwd_ms:
+        dom, dom_ms, dom_bytes = 'backward_kernel', k_bwd_ms, bwd_bytes
+    else:
+        dom, dom_ms, dom_bytes = 'raster_kernel(forward)', k_fwd_ms, fwd_bytes
+    achieved = dom_bytes / (dom_ms * 1e-3) / 1e9
+    roofline = {'bound': 'hbm', 'kernel': dom, 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
+                'traffic': None, 'peak_source': peak_src, 'algorithmic_bytes_per_launch': int(dom_bytes),
+                'kernel_ms': dom_ms,
+                'forward_kernel': {'ms': k_fwd_ms, 'algorithmic_bytes': int(fwd_bytes), 'gbs': fwd_bytes / (k_fwd_ms * 1e-3) / 1e9},
+                'backward_kernel': {'ms': k_bwd_ms, 'algorithmic_bytes': int(bwd_bytes), 'gbs': bwd_bytes / (k_bwd_ms * 1e-3) / 1e9},
+                'step': {'ms': ms_per_step, 'algorithmic_bytes': int(fwd_bytes + bwd_bytes),
+                         'gbs': (fwd_bytes + bwd_bytes) / (ms_per_step * 1e-3) / 1e9,
+                         'frac': (fwd_bytes + bwd_bytes) / (ms_per_step * 1e-3) / 1e9 / peak}}
+
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        mpix, n_img, dt, threads = cpu_baseline(scene, prep.grad_pixels_host, args.cpu_sample)
+        cpu = {'value': mpix, 'unit': UNIT, 'cores': threads, 'kind': 'port',
+               'sample': 'oracle/dirt_oracle.c (OpenMP over images) fwd+bwd on the first %d images of the workload, %.1f s' % (n_img, dt)}
+
+    out = {
+        'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3),
+        'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
+        'data': 'synthetic',
+        'config': {'workload': desc, 'name': args.workload, 'batch_per_gpu': B, 'global_batch': B * world, 'height': H, 'width': W,
+                   'channels': C, 'vertices': V, 'faces': F, 'parallelism': 'batch-sharded x%d' % world,
+                   'collective': 'all_reduce(sum over batch of grad_vertices|grad_vertex_colors, [V,%d] fp32)' % (4 + C) if world > 1 else 'none (N=1)',
+                   'l2': 'inputs larger than L2 (%.0f MB touched per step)' % ((fwd_bytes + bwd_bytes) / 1e6)},
+        'phases_ms': {'forward_call': fwd_ms, 'backward_call': bwd_ms},
+        'gpu_launches': int(launches), 'gpu_launches_per_step': int(prep.launches_per_step),
+        'clocks': clocks, 'roofline': roofline,
+    }
+    if e2e:
+        out['e2e'] = e2e
+    if cpu:
+        out['cpu_baseline'] = cpu
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ---------------------------------------------------------------------------------------------------------
+# reference arm: the CPU port of the reference path (the reference's GL/TF op cannot run in this image)
+# ---------------------------------------------------------------------------------------------------------
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    if rank != 0:
+        return
+    from dirt_b200 import scenes
+    from oracle import oracle
+    oracle.build()
+    gen, kwargs, desc = WORKLOADS[args.workload]
+    kwargs = dict(kwargs)
+    sample = min(args.cpu_sample, kwargs.get('batch', 1))
+    kwargs['batch'] = sample if 'batch' in kwargs else None
+    if kwargs.get('batch') is None:
+        kwargs.pop('batch', None)
+    if args.workload != 'cfg2':
+        kwargs['seed'] = 1
+    scene = getattr(scenes, gen)(**kwargs)
+    B, H, W, C = scene['background'].shape
+    V, F = scene['vertices'].shape[1], scene['faces'].shape[1]
+    gp = np.random.default_rng(2).standard_normal((B, H, W, C)).astype(np.float32)
+
+    def step():
+        pixels = oracle.forward(**scene)
+        oracle.backward(scene['vertices'], scene['faces'], pixels, gp)
+
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = (time.perf_counter() - t0) / args.steps
+    value = B * H * W / dt / 1e6
+    threads = oracle.threads()
+    out = {
+        'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
+        'warmup': args.warmup, 'ms_per_step': dt * 1e3, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': desc, 'name': args.workload, 'sample_images_per_step': B, 'height': H, 'width': W, 'channels': C,
+                   'vertices': V, 'faces': F,
+                   'note': 'the reference OpenGL/TensorFlow op cannot run in this image; this is the CPU port of its path '
+                           '(oracle/dirt_oracle.c, OpenMP over images) on a bounded sample of the same workload'},
+        'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': threads, 'kind': 'port',
+                         'sample': '%d images of the workload per step, %d steps' % (B, args.steps)},
+        'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(out))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--workload', default='cfg3', choices=sorted(WORKLOADS))
+    ap.add_argument('--batch', type=int, default=0, help='override the per-GPU batch (debugging)')
+    ap.add_argument('--cpu-sample', type=int, default=16, help='images the CPU baseline renders')
+    ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == '__main__':
+    main()

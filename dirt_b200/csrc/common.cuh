@@ -1,0 +1,252 @@
+// common.cuh -- record layouts, workspace carving and the exactly-specified arithmetic shared by
+// the sm_100a kernels of libdirt_b200.so.
+//
+// The arithmetic in `exact::` implements the visibility specification S1-S7 / H1-H3 / G written
+// out in DESIGN.md (and restated independently in oracle/dirt_oracle.c): every operation that can
+// change which face a pixel shows is an explicitly rounded intrinsic (__fmul_rn, __dadd_rn, ...)
+// so that nvcc's fused-multiply-add contraction cannot alter it.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace dirt {
+
+constexpr int TILE = 8;                    // screen tile edge in pixels: one warp per 8x8 tile, 2 px per lane
+constexpr int TILE_SHIFT = 3;
+constexpr uint32_t KEY_EMPTY = 0x00800000u; // depth key of the cleared depth buffer (1.0)
+constexpr int SMALL_TILE_LIMIT = 16;       // faces whose bbox spans <= this many tiles are binned per tile;
+                                           // larger ones go to the per-image "large" list
+constexpr int MAX_GROUPS = 128;            // channel groups (each 1 or 3 wide)
+
+// ---- per-face records written by the setup kernel (64 B each, 16-B vector loadable) ------------
+struct __align__(16) TriCov {   // coverage + depth: everything the z-buffer loop needs
+    int32_t A0, B0, A1, B1;     // edge k: n_k(col,row) = A_k*col + B_k*row + q_k >= 0 inside (S5)
+    int32_t A2, B2;
+    float zA, zB;               // depth plane, absolute (col,row) (S6/S7)
+    int64_t q0, q1;
+    int64_t q2;
+    float zC;
+    uint32_t kind;              // 0 culled, 1 normal, 2 hard
+};
+static_assert(sizeof(TriCov) == 64, "TriCov must be 64 bytes");
+
+struct __align__(16) TriInterp { // interpolation planes relative to (cref,rref) + vertex ids (G)
+    float q0A, q0B, q0C, q1A;
+    float q1B, q1C, sA, sB;
+    float sC;
+    int32_t v0, v1, v2;
+    int32_t cref, rref;
+    int32_t pad0, pad1;
+};
+static_assert(sizeof(TriInterp) == 64, "TriInterp must be 64 bytes");
+
+// ---- workspace ---------------------------------------------------------------------------------
+struct Workspace {
+    TriCov* cov;          // [B*F]
+    TriInterp* itp;       // [B*F]
+    uint2* tri_bin;       // [B*F]  tile bbox (tx0|ty0<<16, tx1|ty1<<16); x = 0xFFFFFFFF: not binned per tile
+    int* tile_count;      // [B*T]  per-tile reference count, then reused as the fill cursor
+    int2* tile_range;     // [B*T]  (offset into refs, count)
+    int* large_count;     // [B]
+    int* large_list;      // [B*F]
+    int* pool_cursor;     // [1] (+ padding)
+    int* refs;            // [SMALL_TILE_LIMIT*B*F]
+    int32_t* face_ids;    // [B*H*W] (used when the caller does not supply a buffer)
+    size_t bytes;
+};
+
+__host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+inline Workspace carve_workspace(void* base, int B, int H, int W, int F)
+{
+    Workspace ws;
+    const size_t tiles = (size_t)((W + TILE - 1) / TILE) * ((H + TILE - 1) / TILE);
+    const size_t BF = (size_t)B * F, BT = (size_t)B * tiles;
+    size_t off = 0;
+    char* p = (char*)base;
+    auto take = [&](size_t bytes) { char* r = p + off; off = align_up(off + bytes, 256); return r; };
+    ws.cov = (TriCov*)take(BF * sizeof(TriCov));
+    ws.itp = (TriInterp*)take(BF * sizeof(TriInterp));
+    ws.tri_bin = (uint2*)take(BF * sizeof(uint2));
+    ws.tile_count = (int*)take(BT * sizeof(int));
+    ws.tile_range = (int2*)take(BT * sizeof(int2));
+    ws.large_count = (int*)take((size_t)B * sizeof(int));
+    ws.large_list = (int*)take(BF * sizeof(int));
+    ws.pool_cursor = (int*)take(256);
+    ws.refs = (int*)take(BF * SMALL_TILE_LIMIT * sizeof(int));
+    ws.face_ids = (int32_t*)take((size_t)B * H * W * sizeof(int32_t));
+    ws.bytes = off;
+    return ws;
+}
+
+// ---- exactly specified arithmetic --------------------------------------------------------------
+namespace exact {
+
+__device__ __forceinline__ double dsub(double a, double b) { return __dadd_rn(a, -b); }
+
+// NDC plane (a,b,c) -> pixel-index plane g = (gA,gB,gC)
+__device__ __forceinline__ void ndc_to_pixel_plane(double a, double b, double c, double two_over_W,
+                                                   double two_over_H, double inv_W, double inv_H, double g[3])
+{
+    g[0] = __dmul_rn(a, two_over_W);
+    g[1] = -__dmul_rn(b, two_over_H);
+    double t0 = __dmul_rn(a, dsub(inv_W, 1.0));
+    double t1 = __dmul_rn(b, dsub(1.0, inv_H));
+    g[2] = __dadd_rn(__dadd_rn(t0, t1), c);
+}
+
+// S6: planes of q_k = beta_k/w_k (k=0..2), S = 1/clip_w and window depth, in double, absolute pixel
+// indices.  p[k] = (x,y,z,w) of vertex k.  Returns false when the face is degenerate.
+__device__ inline bool planes_double(const float p[3][4], int H, int W, double gq[3][3], double gs[3], double gz[3])
+{
+    const double x0 = p[0][0], y0 = p[0][1], w0 = p[0][3];
+    const double x1 = p[1][0], y1 = p[1][1], w1 = p[1][3];
+    const double x2 = p[2][0], y2 = p[2][1], w2 = p[2][3];
+    const double c00 = dsub(__dmul_rn(y1, w2), __dmul_rn(y2, w1));
+    const double c01 = dsub(__dmul_rn(y2, w0), __dmul_rn(y0, w2));
+    const double c02 = dsub(__dmul_rn(y0, w1), __dmul_rn(y1, w0));
+    const double c10 = dsub(__dmul_rn(w1, x2), __dmul_rn(w2, x1));
+    const double c11 = dsub(__dmul_rn(w2, x0), __dmul_rn(w0, x2));
+    const double c12 = dsub(__dmul_rn(w0, x1), __dmul_rn(w1, x0));
+    const double c20 = dsub(__dmul_rn(x1, y2), __dmul_rn(x2, y1));
+    const double c21 = dsub(__dmul_rn(x2, y0), __dmul_rn(x0, y2));
+    const double c22 = dsub(__dmul_rn(x0, y1), __dmul_rn(x1, y0));
+    const double det = __dadd_rn(__dadd_rn(__dmul_rn(x0, c00), __dmul_rn(y0, c10)), __dmul_rn(w0, c20));
+    if (!(det != 0.0) || !isfinite(det)) return false;
+    double inv[3][3];
+    inv[0][0] = __ddiv_rn(c00, det); inv[0][1] = __ddiv_rn(c01, det); inv[0][2] = __ddiv_rn(c02, det);
+    inv[1][0] = __ddiv_rn(c10, det); inv[1][1] = __ddiv_rn(c11, det); inv[1][2] = __ddiv_rn(c12, det);
+    inv[2][0] = __ddiv_rn(c20, det); inv[2][1] = __ddiv_rn(c21, det); inv[2][2] = __ddiv_rn(c22, det);
+    const double two_over_W = __ddiv_rn(2.0, (double)W), two_over_H = __ddiv_rn(2.0, (double)H);
+    const double inv_W = __ddiv_rn(1.0, (double)W), inv_H = __ddiv_rn(1.0, (double)H);
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+        ndc_to_pixel_plane(inv[0][k], inv[1][k], inv[2][k], two_over_W, two_over_H, inv_W, inv_H, gq[k]);
+    ndc_to_pixel_plane(__dadd_rn(__dadd_rn(inv[0][0], inv[0][1]), inv[0][2]),
+                       __dadd_rn(__dadd_rn(inv[1][0], inv[1][1]), inv[1][2]),
+                       __dadd_rn(__dadd_rn(inv[2][0], inv[2][1]), inv[2][2]),
+                       two_over_W, two_over_H, inv_W, inv_H, gs);
+    const double z0 = p[0][2], z1 = p[1][2], z2 = p[2][2];
+    const double a = __dadd_rn(__dadd_rn(__dmul_rn(inv[0][0], z0), __dmul_rn(inv[0][1], z1)), __dmul_rn(inv[0][2], z2));
+    const double b = __dadd_rn(__dadd_rn(__dmul_rn(inv[1][0], z0), __dmul_rn(inv[1][1], z1)), __dmul_rn(inv[1][2], z2));
+    const double c = __dadd_rn(__dadd_rn(__dmul_rn(inv[2][0], z0), __dmul_rn(inv[2][1], z1)), __dmul_rn(inv[2][2], z2));
+    double g[3];
+    ndc_to_pixel_plane(a, b, c, two_over_W, two_over_H, inv_W, inv_H, g);
+    gz[0] = __dmul_rn(0.5, g[0]);
+    gz[1] = __dmul_rn(0.5, g[1]);
+    gz[2] = __dadd_rn(__dmul_rn(0.5, g[2]), 0.5);
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+        if (!isfinite(gz[j]) || !isfinite(gs[j]) || !isfinite(gq[0][j]) || !isfinite(gq[1][j]) || !isfinite(gq[2][j]))
+            return false;
+    return true;
+}
+
+// S7: depth key from a window depth z; a fragment exists iff key < KEY_EMPTY
+__device__ __forceinline__ uint32_t depth_key(float z)
+{
+    return __float_as_uint(__fmaf_rn(z, 8388608.0f, 8388608.0f)) - 0x4B000000u;
+}
+
+// S7: depth of a normal face at absolute pixel (col,row)
+__device__ __forceinline__ float depth_normal(float zA, float zB, float zC, float col, float row)
+{
+    return __fmaf_rn(zA, col, __fmaf_rn(zB, row, zC));
+}
+
+// H1: a double plane at absolute (col,row): gA*col + (gB*row + gC)
+__device__ __forceinline__ double plane_double(const double g[3], int col, int row)
+{
+    return __dadd_rn(__dmul_rn(g[0], (double)col), __dadd_rn(__dmul_rn(g[1], (double)row), g[2]));
+}
+
+// G: barycentrics and clip-w of a face at pixel (col,row)
+__device__ __forceinline__ float4 gbuffer_at(const TriInterp& t, int col, int row)
+{
+    const float dc = (float)(col - t.cref), dr = (float)(row - t.rref);
+    const float S = __fmaf_rn(t.sA, dc, __fmaf_rn(t.sB, dr, t.sC));
+    const float cw = __fdiv_rn(1.0f, S);
+    const float q0 = __fmaf_rn(t.q0A, dc, __fmaf_rn(t.q0B, dr, t.q0C));
+    const float q1 = __fmaf_rn(t.q1A, dc, __fmaf_rn(t.q1B, dr, t.q1C));
+    const float b0 = __fmul_rn(q0, cw), b1 = __fmul_rn(q1, cw);
+    return make_float4(b0, b1, __fsub_rn(__fsub_rn(1.0f, b0), b1), cw);
+}
+
+}  // namespace exact
+
+// 64-byte record loads through the read-only path
+__device__ __forceinline__ TriInterp load_interp(const TriInterp* p)
+{
+    union { TriInterp t; uint4 u[4]; } r;
+    const uint4* s = reinterpret_cast<const uint4*>(p);
+    r.u[0] = __ldg(s); r.u[1] = __ldg(s + 1); r.u[2] = __ldg(s + 2); r.u[3] = __ldg(s + 3);
+    return r.t;
+}
+__device__ __forceinline__ TriCov load_cov(const TriCov* p)
+{
+    union { TriCov t; uint4 u[4]; } r;
+    const uint4* s = reinterpret_cast<const uint4*>(p);
+    r.u[0] = __ldg(s); r.u[1] = __ldg(s + 1); r.u[2] = __ldg(s + 2); r.u[3] = __ldg(s + 3);
+    return r.t;
+}
+
+// ---- launch parameter blocks -------------------------------------------------------------------
+struct Dims {
+    int B, H, W, C, V, F;
+    int tiles_x, tiles_y, tiles;  // per image
+};
+
+inline Dims make_dims(int B, int H, int W, int C, int V, int F)
+{
+    Dims d;
+    d.B = B; d.H = H; d.W = W; d.C = C; d.V = V; d.F = F;
+    d.tiles_x = (W + TILE - 1) / TILE;
+    d.tiles_y = (H + TILE - 1) / TILE;
+    d.tiles = d.tiles_x * d.tiles_y;
+    return d;
+}
+
+struct GroupSpec {
+    int n;
+    unsigned char width[MAX_GROUPS];
+};
+
+// ---- optional per-kernel timing (dirt_kernel_timer_enable) -------------------------------------
+struct KernelTimer {
+    int which = 0;  // 0 off, 1 forward raster kernel, 2 backward kernel
+    cudaEvent_t start = nullptr, stop = nullptr;
+    bool recorded = false;
+};
+KernelTimer& kernel_timer();  // thread-local, defined in api.cu
+
+struct ScopedKernelTimer {
+    KernelTimer& t;
+    cudaStream_t stream;
+    bool on;
+    ScopedKernelTimer(int which, cudaStream_t s) : t(kernel_timer()), stream(s), on(t.which == which && t.start)
+    {
+        if (on) cudaEventRecord(t.start, stream);
+    }
+    ~ScopedKernelTimer()
+    {
+        if (on) { cudaEventRecord(t.stop, stream); t.recorded = true; }
+    }
+};
+
+// ---- host-side launchers (one per .cu) ----------------------------------------------------------
+// All return cudaError_t of the launch and add the number of kernels they launched to *launches.
+cudaError_t launch_setup_and_bin(const float* vertices, const int32_t* faces, const Workspace& ws, const Dims& d,
+                                 cudaStream_t stream, int* launches);
+cudaError_t launch_setup_only(const float* vertices, const int32_t* faces, const Workspace& ws, const Dims& d,
+                              cudaStream_t stream, int* launches);
+cudaError_t launch_raster_forward(const float* vertices, const float* background, const float* vertex_colors, float* pixels,
+                                  int32_t* face_ids_out, const Workspace& ws, const Dims& d, cudaStream_t stream,
+                                  int* launches);
+cudaError_t launch_raster_visibility(const float* vertices, int32_t* face_ids, float* gbuffer, const Workspace& ws, const Dims& d,
+                                     cudaStream_t stream, int* launches);
+cudaError_t launch_backward(const float* vertices, const float* pixels, const float* grad_pixels,
+                            const int32_t* face_ids, float* grad_background, float* grad_vertices,
+                            float* grad_vertex_colors, const Workspace& ws, const Dims& d, const GroupSpec& groups,
+                            cudaStream_t stream, int* launches);
+
+}  // namespace dirt

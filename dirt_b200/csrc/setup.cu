@@ -1,0 +1,261 @@
+// setup.cu -- triangle setup and per-tile binning.
+//
+// Replaces, for the sm_100a path, what the reference delegates to the OpenGL vertex pipeline
+// (clip -> NDC -> viewport; csrc/rasterise_egl.cpp:362-380) and the vertex expansion kernel
+// upload_vertices (csrc/rasterise_grad_egl.cu:12-34).
+//
+//   setup_kernel : one thread per (image, face): S1-S6 of the visibility specification ->
+//                  TriCov + TriInterp records, tile bounding box, per-tile reference counts
+//                  (faces spanning <= SMALL_TILE_LIMIT tiles) or the per-image large list.
+//   scan_kernel  : turns per-tile counts into (offset,count) ranges in the reference pool
+//                  (block-local exclusive scan + one atomic per block; list order is irrelevant
+//                  because visibility is the minimum of (depth key, face index)).
+//   fill_kernel  : one thread per (image, face): writes the face index into each tile's range.
+#include "common.cuh"
+
+namespace dirt {
+
+constexpr float GUARD_BAND = 8388608.0f;  // 2^23 sub-pixel units = 32768 px
+
+template <bool BIN>
+__global__ void __launch_bounds__(256) setup_kernel(const float* __restrict__ vertices,
+                                                    const int32_t* __restrict__ faces, Workspace ws, Dims d)
+{
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long total = (long long)d.B * d.F;
+    if (gid >= total) return;
+    const int b = (int)(gid / d.F);
+    const int f = (int)(gid - (long long)b * d.F);
+    const float* verts = vertices + (size_t)b * d.V * 4;
+
+    TriCov cov;
+    TriInterp itp;
+    cov.A0 = cov.B0 = cov.A1 = cov.B1 = cov.A2 = cov.B2 = 0;
+    cov.q0 = cov.q1 = cov.q2 = -1;
+    cov.zA = cov.zB = cov.zC = 0.f;
+    cov.kind = 0;
+    itp.q0A = itp.q0B = itp.q0C = itp.q1A = itp.q1B = itp.q1C = itp.sA = itp.sB = 0.f;
+    itp.sC = 1.f;
+    itp.v0 = itp.v1 = itp.v2 = 0;
+    itp.cref = itp.rref = 0;
+    itp.pad0 = itp.pad1 = 0;
+    uint2 bin = make_uint2(0xFFFFFFFFu, 0xFFFFFFFFu);
+
+    int kind = 0;
+    float p[3][4];
+    int32_t vid[3];
+    bool ok = true;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        vid[k] = __ldg(&faces[(size_t)gid * 3 + k]);
+        if (vid[k] < 0 || vid[k] >= d.V) ok = false;
+    }
+    if (ok) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const float4 v = __ldg(reinterpret_cast<const float4*>(verts) + vid[k]);
+            p[k][0] = v.x; p[k][1] = v.y; p[k][2] = v.z; p[k][3] = v.w;
+            if (!isfinite(v.x) || !isfinite(v.y) || !isfinite(v.z) || !isfinite(v.w)) ok = false;
+        }
+    }
+    int cmin = 0, cmax = -1, rmin = 0, rmax = -1;
+    if (ok) {
+        bool hard = false;
+        int n_behind = 0;
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+            if (!(p[k][3] > 0.0f)) { hard = true; ++n_behind; }
+        if (n_behind == 3) ok = false;
+
+        int32_t xi[3] = {0, 0, 0}, yi[3] = {0, 0, 0};
+        if (ok && !hard) {
+            const float halfW = 0.5f * (float)d.W, halfH = 0.5f * (float)d.H;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const float xn = __fdiv_rn(p[k][0], p[k][3]);
+                const float yn = __fdiv_rn(p[k][1], p[k][3]);
+                const float X = __fmul_rn(__fadd_rn(xn, 1.0f), halfW);
+                const float Y = __fmul_rn(__fsub_rn(1.0f, yn), halfH);
+                const float fx = __fmul_rn(X, 256.0f), fy = __fmul_rn(Y, 256.0f);
+                if (!(fabsf(fx) <= GUARD_BAND) || !(fabsf(fy) <= GUARD_BAND)) hard = true;
+                else { xi[k] = __float2int_rn(fx); yi[k] = __float2int_rn(fy); }
+            }
+        }
+        double gq[3][3], gs[3], gz[3];
+        if (ok) ok = exact::planes_double(p, d.H, d.W, gq, gs, gz);
+        if (ok) {
+            if (hard) {
+                kind = 2;
+                cmin = 0; cmax = d.W - 1; rmin = 0; rmax = d.H - 1;
+            } else {
+                const int64_t ax = xi[0], ay = yi[0], bx = xi[1], by = yi[1], cx = xi[2], cy = yi[2];
+                const int64_t area2 = (bx - ax) * (cy - ay) - (cx - ax) * (by - ay);
+                if (area2 == 0) ok = false;
+                else {
+                    int32_t px[3] = {xi[0], xi[1], xi[2]}, py[3] = {yi[0], yi[1], yi[2]};
+                    if (area2 < 0) {
+                        int32_t t = px[1]; px[1] = px[2]; px[2] = t;
+                        t = py[1]; py[1] = py[2]; py[2] = t;
+                    }
+                    int32_t A[3], Bc[3];
+                    int64_t q[3];
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) {
+                        const int a = (k + 1) % 3, bb = (k + 2) % 3;
+                        const int64_t Ak = (int64_t)py[a] - py[bb];
+                        const int64_t Bk = (int64_t)px[bb] - px[a];
+                        const int64_t Ck = -(Ak * px[a] + Bk * py[a]);
+                        const bool tl = (Ak > 0) || (Ak == 0 && Bk > 0);
+                        const int64_t Cpp = 128 * (Ak + Bk) + Ck - (tl ? 0 : 1);
+                        A[k] = (int32_t)Ak; Bc[k] = (int32_t)Bk; q[k] = Cpp >> 8;
+                    }
+                    const int32_t xmin = min(px[0], min(px[1], px[2])), xmax = max(px[0], max(px[1], px[2]));
+                    const int32_t ymin = min(py[0], min(py[1], py[2])), ymax = max(py[0], max(py[1], py[2]));
+                    cmin = max((xmin + 127) >> 8, 0); cmax = min((xmax - 128) >> 8, d.W - 1);
+                    rmin = max((ymin + 127) >> 8, 0); rmax = min((ymax - 128) >> 8, d.H - 1);
+                    if (cmin > cmax || rmin > rmax) ok = false;
+                    else {
+                        kind = 1;
+                        cov.A0 = A[0]; cov.B0 = Bc[0]; cov.q0 = q[0];
+                        cov.A1 = A[1]; cov.B1 = Bc[1]; cov.q1 = q[1];
+                        cov.A2 = A[2]; cov.B2 = Bc[2]; cov.q2 = q[2];
+                    }
+                }
+            }
+        }
+        if (ok) {
+            const int cref = (kind == 1) ? cmin : 0, rref = (kind == 1) ? rmin : 0;
+            const double cr = (double)cref, rr = (double)rref;
+            cov.zA = (float)gz[0]; cov.zB = (float)gz[1]; cov.zC = (float)gz[2];
+            cov.kind = (uint32_t)kind;
+            itp.q0A = (float)gq[0][0]; itp.q0B = (float)gq[0][1];
+            itp.q0C = (float)__dadd_rn(__dadd_rn(__dmul_rn(gq[0][0], cr), __dmul_rn(gq[0][1], rr)), gq[0][2]);
+            itp.q1A = (float)gq[1][0]; itp.q1B = (float)gq[1][1];
+            itp.q1C = (float)__dadd_rn(__dadd_rn(__dmul_rn(gq[1][0], cr), __dmul_rn(gq[1][1], rr)), gq[1][2]);
+            itp.sA = (float)gs[0]; itp.sB = (float)gs[1];
+            itp.sC = (float)__dadd_rn(__dadd_rn(__dmul_rn(gs[0], cr), __dmul_rn(gs[1], rr)), gs[2]);
+            itp.v0 = vid[0]; itp.v1 = vid[1]; itp.v2 = vid[2];
+            itp.cref = cref; itp.rref = rref;
+        }
+    }
+    if (!ok) { kind = 0; cov.kind = 0; }
+
+    // records (64-B stores as 4 x 16 B)
+    {
+        union { TriCov t; uint4 u[4]; } c; c.t = cov;
+        uint4* dst = reinterpret_cast<uint4*>(ws.cov + gid);
+        dst[0] = c.u[0]; dst[1] = c.u[1]; dst[2] = c.u[2]; dst[3] = c.u[3];
+        union { TriInterp t; uint4 u[4]; } i; i.t = itp;
+        uint4* dsti = reinterpret_cast<uint4*>(ws.itp + gid);
+        dsti[0] = i.u[0]; dsti[1] = i.u[1]; dsti[2] = i.u[2]; dsti[3] = i.u[3];
+    }
+    if (!BIN) return;
+
+    if (kind != 0) {
+        const int tx0 = cmin >> TILE_SHIFT, tx1 = cmax >> TILE_SHIFT;
+        const int ty0 = rmin >> TILE_SHIFT, ty1 = rmax >> TILE_SHIFT;
+        const int ntiles = (tx1 - tx0 + 1) * (ty1 - ty0 + 1);
+        if (kind == 1 && ntiles <= SMALL_TILE_LIMIT) {
+            bin = make_uint2((uint32_t)tx0 | ((uint32_t)ty0 << 16), (uint32_t)tx1 | ((uint32_t)ty1 << 16));
+            int* counts = ws.tile_count + (size_t)b * d.tiles;
+            for (int ty = ty0; ty <= ty1; ++ty)
+                for (int tx = tx0; tx <= tx1; ++tx) atomicAdd(&counts[ty * d.tiles_x + tx], 1);
+        } else {
+            const int pos = atomicAdd(&ws.large_count[b], 1);
+            ws.large_list[(size_t)b * d.F + pos] = f;
+        }
+    }
+    ws.tri_bin[gid] = bin;
+}
+
+// per-tile counts -> (offset,count); zeroes the count so fill_kernel can reuse it as a cursor
+__global__ void __launch_bounds__(1024) scan_kernel(Workspace ws, long long total_tiles)
+{
+    __shared__ int warp_sums[32];
+    __shared__ int block_base;
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int count = 0;
+    if (gid < total_tiles) count = ws.tile_count[gid];
+    int incl = count;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+    }
+    if (lane == 31) warp_sums[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        int w = warp_sums[lane];
+        int wi = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, wi, o);
+            if (lane >= o) wi += v;
+        }
+        warp_sums[lane] = wi - w;  // exclusive
+        if (lane == 31) block_base = atomicAdd(ws.pool_cursor, wi);
+    }
+    __syncthreads();
+    if (gid < total_tiles) {
+        const int offset = block_base + warp_sums[warp] + incl - count;
+        ws.tile_range[gid] = make_int2(offset, count);
+        ws.tile_count[gid] = 0;
+    }
+}
+
+__global__ void __launch_bounds__(256) fill_kernel(Workspace ws, Dims d)
+{
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long total = (long long)d.B * d.F;
+    if (gid >= total) return;
+    const uint2 bin = ws.tri_bin[gid];
+    if (bin.x == 0xFFFFFFFFu) return;
+    const int b = (int)(gid / d.F);
+    const int f = (int)(gid - (long long)b * d.F);
+    const int tx0 = bin.x & 0xFFFF, ty0 = bin.x >> 16, tx1 = bin.y & 0xFFFF, ty1 = bin.y >> 16;
+    const size_t tbase = (size_t)b * d.tiles;
+    for (int ty = ty0; ty <= ty1; ++ty)
+        for (int tx = tx0; tx <= tx1; ++tx) {
+            const size_t t = tbase + (size_t)ty * d.tiles_x + tx;
+            const int pos = atomicAdd(&ws.tile_count[t], 1);
+            ws.refs[ws.tile_range[t].x + pos] = f;
+        }
+}
+
+cudaError_t launch_setup_and_bin(const float* vertices, const int32_t* faces, const Workspace& ws, const Dims& d,
+                                 cudaStream_t stream, int* launches)
+{
+    const long long total = (long long)d.B * d.F;
+    const long long total_tiles = (long long)d.B * d.tiles;
+    cudaError_t e;
+    if ((e = cudaMemsetAsync(ws.tile_count, 0, sizeof(int) * (size_t)total_tiles, stream)) != cudaSuccess) return e;
+    if ((e = cudaMemsetAsync(ws.large_count, 0, sizeof(int) * (size_t)d.B, stream)) != cudaSuccess) return e;
+    if ((e = cudaMemsetAsync(ws.pool_cursor, 0, 256, stream)) != cudaSuccess) return e;
+    if (total > 0) {
+        setup_kernel<true><<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(vertices, faces, ws, d);
+        ++*launches;
+    }
+    if (total_tiles > 0) {
+        scan_kernel<<<(unsigned)((total_tiles + 1023) / 1024), 1024, 0, stream>>>(ws, total_tiles);
+        ++*launches;
+    }
+    if (total > 0) {
+        fill_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(ws, d);
+        ++*launches;
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_setup_only(const float* vertices, const int32_t* faces, const Workspace& ws, const Dims& d,
+                              cudaStream_t stream, int* launches)
+{
+    const long long total = (long long)d.B * d.F;
+    if (total > 0) {
+        setup_kernel<false><<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(vertices, faces, ws, d);
+        ++*launches;
+    }
+    return cudaGetLastError();
+}
+
+}  // namespace dirt

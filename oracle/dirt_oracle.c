@@ -419,9 +419,11 @@ int dirt_oracle_forward(const float* background, const float* vertices, const fl
                     tri_gbuffer(&tris[f], c, r, g);
                     const Tri* t = &tris[f];
                     for (int ch = 0; ch < C; ++ch) {
-                        double acc = (double)g[0] * cols[(size_t)t->v[0] * C + ch] +
-                                     (double)g[1] * cols[(size_t)t->v[1] * C + ch] +
-                                     (double)g[2] * cols[(size_t)t->v[2] * C + ch];
+                        /* c2 + b0*(c0-c2) + b1*(c1-c2): exact when the three vertex colours are equal, as
+                         * tests/square_test.py requires of the hardware interpolator */
+                        double c0 = cols[(size_t)t->v[0] * C + ch], c1 = cols[(size_t)t->v[1] * C + ch];
+                        double c2 = cols[(size_t)t->v[2] * C + ch];
+                        double acc = c2 + ((double)g[0] * (c0 - c2) + (double)g[1] * (c1 - c2));
                         pixels[pix * C + ch] = (float)acc;
                     }
                 }

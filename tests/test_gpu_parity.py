@@ -1,0 +1,204 @@
+"""GPU: the CUDA path (through the C ABI) against the CPU oracle on the same seeded inputs.
+
+Bar (BASELINE.json north_star / SURVEY 8c): face/pixel indexing bit-exact; float pixels and gradients
+within 1e-4 relative (rel_close in conftest.py: |a-b| <= 1e-4 * max(|a|, |b|, 1e-2 * max|oracle|)).
+"""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import rel_close
+from dirt_b200 import scenes
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = os.path.join(os.path.dirname(__file__), 'golden')
+
+
+def _cuda(s):
+    import torch
+    return {k: torch.from_numpy(v).cuda() for k, v in s.items()}
+
+
+def _forward(s):
+    from dirt_b200 import rasterise_ops as ops
+    t = _cuda(s)
+    pixels, ids = ops.rasterise_forward_raw(t['background'], t['vertices'], t['vertex_colors'], t['faces'])
+    return pixels.cpu().numpy(), ids.cpu().numpy()
+
+
+def _backward(s, pixels, grad_pixels, with_ids=None, groups=None):
+    import torch
+    from dirt_b200 import rasterise_ops as ops
+    t = _cuda(s)
+    ids = None if with_ids is None else torch.from_numpy(with_ids).cuda()
+    gb, gv, gc = ops.rasterise_backward_raw(t['vertices'], t['faces'], torch.from_numpy(pixels).cuda(),
+                                            torch.from_numpy(grad_pixels).cuda(), ids, groups)
+    return gb.cpu().numpy(), gv.cpu().numpy(), gc.cpu().numpy()
+
+
+def _check_scene(oracle, s, seed=0, groups=None, label=''):
+    H, W = s['background'].shape[1:3]
+    pixels_o, ids_o = oracle.forward(**s, return_face_ids=True)
+    pixels_g, ids_g = _forward(s)
+    np.testing.assert_array_equal(ids_g, ids_o, err_msg=label + ': face ids differ')
+    ok, ratio = rel_close(pixels_g, pixels_o)
+    assert ok, '%s: pixels off by %.2fx the tolerance' % (label, ratio)
+    gp = np.random.default_rng(seed).standard_normal(pixels_o.shape).astype(np.float32)
+    gb_o, gv_o, gc_o = oracle.backward(s['vertices'], s['faces'], pixels_o, gp, groups)
+    for ids_arg in (ids_g, None):   # cached visibility, and re-derived inside the call
+        gb_g, gv_g, gc_g = _backward(s, pixels_o, gp, ids_arg, groups)
+        np.testing.assert_array_equal(gb_g, gb_o, err_msg=label + ': grad_background differs')
+        for name, a, b in (('grad_vertices', gv_g, gv_o), ('grad_vertex_colors', gc_g, gc_o)):
+            ok, ratio = rel_close(a, b)
+            assert ok, '%s: %s off by %.2fx the tolerance' % (label, name, ratio)
+        assert (gv_g[..., 2] == 0).all()
+    return pixels_g, ids_g
+
+
+def test_square_golden_exact(cuda_lib):
+    # BASELINE cfg1: tests/square_test.py, exact equality of all 16384 pixels
+    pixels, ids = _forward(scenes.square_scene())
+    np.testing.assert_array_equal(pixels[0, :, :, 0], np.load(os.path.join(GOLDEN, 'square_test_expected.npy')))
+
+
+def test_public_api_square(cuda_lib):
+    import dirt_b200 as dirt
+    s = scenes.square_scene()
+    pixels = dirt.rasterise(s['background'][0], s['vertices'][0], s['vertex_colors'][0], s['faces'][0],
+                            height=128, width=128, channels=1)
+    assert pixels.is_cuda and tuple(pixels.shape) == (128, 128, 1)
+    np.testing.assert_array_equal(pixels[:, :, 0].cpu().numpy(), np.load(os.path.join(GOLDEN, 'square_test_expected.npy')))
+
+
+@pytest.mark.parametrize('name,kwargs', [
+    ('square_scene', dict(width=64, height=48, centre_x=20, centre_y=30, size=12)),
+    ('cylinder_scene', dict()),
+    ('cylinder_scene', dict(batch=2, seed=3)),
+    ('bent_square_scene', dict(channels=3)),
+    ('bent_square_scene', dict(channels=1)),
+    ('bent_square_scene', dict(channels=4)),
+    ('bent_square_scene', dict(channels=7)),
+    ('bent_square_scene', dict(channels=2, width=37, height=29)),
+    ('cube_scene', dict(width=160, height=120)),
+    ('config2', dict()),
+])
+def test_reference_scenes(cuda_lib, oracle, name, kwargs):
+    _check_scene(oracle, getattr(scenes, name)(**kwargs), label=name)
+
+
+@pytest.mark.parametrize('seed', [0, 1, 2])
+@pytest.mark.parametrize('channels', [1, 3, 4, 5])
+def test_random_soup(cuda_lib, oracle, seed, channels):
+    s = scenes.random_soup(batch=2, width=61, height=45, n_faces=70, channels=channels, seed=seed)
+    _check_scene(oracle, s, seed=seed, label='soup')
+
+
+@pytest.mark.parametrize('seed', [0, 1])
+def test_behind_camera_and_guard_band(cuda_lib, oracle, seed):
+    s = scenes.random_soup(batch=2, width=64, height=48, n_faces=40, channels=3, seed=10 + seed, behind_camera=True)
+    _check_scene(oracle, s, seed=seed, label='behind-camera soup')
+    # push some vertices far outside the guard band (>32768 px)
+    s['vertices'][:, ::7, 0] *= 4000.0
+    _check_scene(oracle, s, seed=seed, label='guard-band soup')
+
+
+def test_reduced_configs(cuda_lib, oracle):
+    _check_scene(oracle, scenes.config3(batch=3, width=160, height=128, level=3, background='uniform'), label='cfg3-small')
+    _check_scene(oracle, scenes.config4(batch=2, width=128, height=128, level=3), label='cfg4-small')
+    _check_scene(oracle, scenes.config5(batch=1, width=256, height=256, n_long=96, n_lat=48), label='cfg5-small')
+
+
+def test_large_faces_and_many_faces_per_tile(cuda_lib, oracle):
+    # faces larger than the per-tile binning limit (large list) mixed with > 32 small faces in one tile (chunking)
+    rng = np.random.default_rng(4)
+    s = scenes.random_soup(batch=1, width=96, height=80, n_faces=30, channels=3, seed=7)
+    n = 200
+    tiny_xy = rng.uniform(-0.12, 0.12, size=(n * 3, 2))
+    tiny = np.concatenate([tiny_xy, rng.uniform(-0.9, 0.9, size=(n * 3, 1)), np.ones((n * 3, 1))], axis=1).astype(np.float32)
+    V0 = s['vertices'].shape[1]
+    s['vertices'] = np.concatenate([s['vertices'], tiny[None]], axis=1)
+    s['vertex_colors'] = np.concatenate([s['vertex_colors'], rng.uniform(size=(1, n * 3, 3)).astype(np.float32)], axis=1)
+    s['faces'] = np.concatenate([s['faces'], (V0 + np.arange(n * 3, dtype=np.int32)).reshape(1, n, 3)], axis=1)
+    _check_scene(oracle, s, label='large+dense')
+
+
+def test_edge_cases(cuda_lib, oracle):
+    s = scenes.square_scene(32, 32, 16, 16, 8)
+    # no faces at all: output is the background, gradients flow to the background only
+    empty = dict(s, faces=np.zeros((1, 0, 3), np.int32))
+    _check_scene(oracle, empty, label='no faces')
+    # degenerate, out-of-range and NaN faces are ignored, not faulted on
+    bad = dict(s)
+    bad['faces'] = np.concatenate([s['faces'], np.array([[[0, 0, 1], [0, 1, 99], [-1, 1, 2]]], np.int32)], axis=1)
+    _check_scene(oracle, bad, label='bad faces')
+    nan = dict(s)
+    nan['vertices'] = np.concatenate([s['vertices'], np.full((1, 1, 4), np.nan, np.float32)], axis=1)
+    nan['vertex_colors'] = np.concatenate([s['vertex_colors'], np.ones((1, 1, 1), np.float32)], axis=1)
+    nan['faces'] = np.concatenate([s['faces'], np.array([[[0, 1, 4]]], np.int32)], axis=1)
+    _check_scene(oracle, nan, label='nan vertex')
+    # frame sizes that are not multiples of the 8x8 tile, and a 1x1 frame
+    _check_scene(oracle, scenes.random_soup(batch=1, width=13, height=7, n_faces=12, channels=3, seed=1), label='13x7')
+    _check_scene(oracle, scenes.random_soup(batch=1, width=1, height=1, n_faces=5, channels=1, seed=2), label='1x1')
+
+
+def test_visibility_gbuffer_matches_oracle(cuda_lib, oracle):
+    import torch
+    from dirt_b200 import rasterise_ops as ops
+    s = scenes.random_soup(batch=2, width=64, height=48, n_faces=50, channels=3, seed=21, behind_camera=True)
+    ids_o, gbuf_o = oracle.visibility(s['vertices'], s['faces'], 48, 64)
+    t = _cuda(s)
+    ids_g, gbuf_g = ops.rasterise_visibility_raw(t['vertices'], t['faces'], 48, 64)
+    np.testing.assert_array_equal(ids_g.cpu().numpy(), ids_o)
+    # the G-buffer arithmetic is fully specified (rule G): bit-identical, not merely close
+    np.testing.assert_array_equal(gbuf_g.cpu().numpy(), gbuf_o)
+
+
+def test_autograd_through_public_api(cuda_lib, oracle):
+    import torch
+    import dirt_b200 as dirt
+    s = scenes.bent_square_scene(channels=4)
+    t = _cuda(s)
+    for k in ('background', 'vertices', 'vertex_colors'):
+        t[k].requires_grad_(True)
+    pixels = dirt.rasterise_batch(t['background'], t['vertices'], t['vertex_colors'], t['faces'])
+    gp = torch.from_numpy(np.random.default_rng(0).standard_normal(tuple(pixels.shape)).astype(np.float32)).cuda()
+    (pixels * gp).sum().backward()
+    pixels_o = oracle.forward(**s)
+    gb_o, gv_o, gc_o = oracle.backward(s['vertices'], s['faces'], pixels_o, gp.cpu().numpy())
+    assert rel_close(pixels.detach().cpu().numpy(), pixels_o)[0]
+    np.testing.assert_array_equal(t['background'].grad.cpu().numpy(), gb_o)
+    assert rel_close(t['vertices'].grad.cpu().numpy(), gv_o)[0]
+    assert rel_close(t['vertex_colors'].grad.cpu().numpy(), gc_o)[0]
+
+
+def test_deferred_matches_reference_recipe(cuda_lib, oracle):
+    # rasterise_deferred: vertex gradient from the SHADED pixels, attribute/background gradients through shader_fn
+    # (dirt/rasterise_ops.py:180-257); compared with the same recipe evaluated with the oracle + torch autograd on CPU
+    import torch
+    import dirt_b200 as dirt
+    s = scenes.bent_square_scene(channels=7, seed=5)
+    t = _cuda(s)
+    for k in ('background', 'vertices', 'vertex_colors'):
+        t[k].requires_grad_(True)
+    light = torch.tensor([0.3, 0.5, 0.8], device='cuda', requires_grad=True)
+
+    def shader_fn(gbuffer, light):
+        return gbuffer[..., :3] * (gbuffer[..., 3:6] * light).sum(-1, keepdim=True).abs() + 0.1 * gbuffer[..., 6:]
+
+    pixels = dirt.rasterise_batch_deferred(t['background'], t['vertices'], t['vertex_colors'], t['faces'], shader_fn, [light])
+    gp = torch.from_numpy(np.random.default_rng(0).standard_normal(tuple(pixels.shape)).astype(np.float32)).cuda()
+    (pixels * gp).sum().backward()
+
+    gbuf_o = torch.from_numpy(oracle.forward(**s)).requires_grad_(True)
+    light_o = light.detach().cpu().requires_grad_(True)
+    pix_o = shader_fn(gbuf_o, light_o)
+    assert rel_close(pixels.detach().cpu().numpy(), pix_o.detach().numpy())[0]
+    d_gbuf, d_light = torch.autograd.grad(pix_o, [gbuf_o, light_o], gp.cpu())
+    _, gv_o, _ = oracle.backward(s['vertices'], s['faces'], pix_o.detach().numpy(), gp.cpu().numpy())
+    gb_o, _, gc_o = oracle.backward(s['vertices'], s['faces'], gbuf_o.detach().numpy(), d_gbuf.numpy())
+    assert rel_close(t['vertices'].grad.cpu().numpy(), gv_o)[0]
+    assert rel_close(t['vertex_colors'].grad.cpu().numpy(), gc_o)[0]
+    assert rel_close(t['background'].grad.cpu().numpy(), gb_o)[0]
+    assert rel_close(light.grad.cpu().numpy(), d_light.numpy(), rel=1e-3)[0]
