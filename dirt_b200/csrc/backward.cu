@@ -11,6 +11,7 @@
 namespace dirt {
 
 constexpr int BWD_WARPS_PER_BLOCK = 4;
+constexpr int TILE = 8;   // backward tile edge: one warp per 8x8 tile, two pixels per lane
 
 struct V3 { float x, y, z; };
 
@@ -56,10 +57,10 @@ __global__ void __launch_bounds__(BWD_WARPS_PER_BLOCK * 32) backward_generic_ker
 {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long tile_global = (long long)blockIdx.x * BWD_WARPS_PER_BLOCK + warp;
-    if (tile_global >= (long long)d.B * d.tiles) return;
-    const int b = (int)(tile_global / d.tiles);
-    const int t = (int)(tile_global - (long long)b * d.tiles);
-    const int ty = t / d.tiles_x, tx = t - ty * d.tiles_x;
+    if (tile_global >= (long long)d.B * d.btiles) return;
+    const int b = (int)(tile_global / d.btiles);
+    const int t = (int)(tile_global - (long long)b * d.btiles);
+    const int ty = t / d.btiles_x, tx = t - ty * d.btiles_x;
     const int col = tx * TILE + (lane & 7), row0 = ty * TILE + (lane >> 3) * 2;
     if (col >= d.W) return;
 
@@ -351,10 +352,10 @@ __global__ void __launch_bounds__(BWD_WARPS_PER_BLOCK * 32) backward_tile_kernel
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long tile_global = (long long)blockIdx.x * BWD_WARPS_PER_BLOCK + warp;
-    if (tile_global >= (long long)d.B * d.tiles) return;
-    const int b = (int)(tile_global / d.tiles);
-    const int t = (int)(tile_global - (long long)b * d.tiles);
-    const int ty = t / d.tiles_x, tx = t - ty * d.tiles_x;
+    if (tile_global >= (long long)d.B * d.btiles) return;
+    const int b = (int)(tile_global / d.btiles);
+    const int t = (int)(tile_global - (long long)b * d.btiles);
+    const int ty = t / d.btiles_x, tx = t - ty * d.btiles_x;
     const int col = tx * TILE + (lane & 7), row0 = ty * TILE + (lane >> 3) * 2;
 
     const TriInterp* itp_b = ws.itp + (size_t)b * d.F;
@@ -507,7 +508,7 @@ cudaError_t launch_backward(const float* vertices, const float* pixels, const fl
     cudaError_t e;
     if ((e = cudaMemsetAsync(grad_vertices, 0, sizeof(float) * (size_t)d.B * d.V * 4, stream)) != cudaSuccess) return e;
     if ((e = cudaMemsetAsync(grad_vertex_colors, 0, sizeof(float) * (size_t)d.B * d.V * d.C, stream)) != cudaSuccess) return e;
-    const long long total_tiles = (long long)d.B * d.tiles;
+    const long long total_tiles = (long long)d.B * d.btiles;
     if (total_tiles == 0) return cudaSuccess;
     const unsigned grid = (unsigned)((total_tiles + BWD_WARPS_PER_BLOCK - 1) / BWD_WARPS_PER_BLOCK);
     ScopedKernelTimer timer(2, stream);

@@ -11,23 +11,32 @@
 
 namespace dirt {
 
-constexpr int TILE = 8;                    // screen tile edge in pixels: one warp per 8x8 tile, 2 px per lane
-constexpr int TILE_SHIFT = 3;
+constexpr int TILE_W = 16;                 // forward raster / binning tile: one warp per 16x8 tile, a 2x2 quad per lane
+constexpr int TILE_H = 8;
+constexpr int TILE_W_SHIFT = 4;
+constexpr int TILE_H_SHIFT = 3;
 constexpr uint32_t KEY_EMPTY = 0x00800000u; // depth key of the cleared depth buffer (1.0)
 constexpr int SMALL_TILE_LIMIT = 16;       // faces whose bbox spans <= this many tiles are binned per tile;
                                            // larger ones go to the per-image "large" list
 constexpr int MAX_GROUPS = 128;            // channel groups (each 1 or 3 wide)
 
+constexpr uint32_t KIND_CULLED = 0, KIND_SMALL = 1, KIND_HARD = 2, KIND_LARGE = 3;
+
 // ---- per-face records written by the setup kernel (64 B each, 16-B vector loadable) ------------
-struct __align__(16) TriCov {   // coverage + depth: everything the z-buffer loop needs
-    int32_t A0, B0, A1, B1;     // edge k: n_k(col,row) = A_k*col + B_k*row + q_k >= 0 inside (S5)
+// Coverage + depth: everything the z-buffer loop needs.  Edge k: n_k(col,row) = A_k*col + B_k*row + q_k >= 0
+// inside (S5); depth plane (zA,zB,zC) in absolute (col,row) (S6/S7).  Two layouts share the 64 bytes:
+//   KIND_SMALL (binned per tile): q relative to the bbox corner (cref,rref) so that everything the raster loop
+//              does fits int32;
+//   KIND_LARGE / KIND_HARD: absolute int64 q (hard faces only use the depth plane and the vertex ids).
+struct __align__(16) TriCov {
+    int32_t A0, B0, A1, B1;
     int32_t A2, B2;
-    float zA, zB;               // depth plane, absolute (col,row) (S6/S7)
-    int64_t q0, q1;
-    int64_t q2;
-    float zC;
-    uint32_t kind;              // 0 culled, 1 normal, 2 hard
+    union {
+        struct { int32_t q0r, q1r, q2r; float zA, zB, zC; int32_t cref, rref, pad; uint32_t kind; } s;
+        struct { float zA, zB; int64_t q0, q1, q2; float zC; uint32_t kind; } l;   // `kind` sits at byte 60 in both
+    };
 };
+#define DIRT_COV_KIND(c) ((c).s.kind)
 static_assert(sizeof(TriCov) == 64, "TriCov must be 64 bytes");
 
 struct __align__(16) TriInterp { // interpolation planes relative to (cref,rref) + vertex ids (G)
@@ -60,7 +69,7 @@ __host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a -
 inline Workspace carve_workspace(void* base, int B, int H, int W, int F)
 {
     Workspace ws;
-    const size_t tiles = (size_t)((W + TILE - 1) / TILE) * ((H + TILE - 1) / TILE);
+    const size_t tiles = (size_t)((W + TILE_W - 1) / TILE_W) * ((H + TILE_H - 1) / TILE_H);
     const size_t BF = (size_t)B * F, BT = (size_t)B * tiles;
     size_t off = 0;
     char* p = (char*)base;
@@ -193,16 +202,20 @@ __device__ __forceinline__ TriCov load_cov(const TriCov* p)
 // ---- launch parameter blocks -------------------------------------------------------------------
 struct Dims {
     int B, H, W, C, V, F;
-    int tiles_x, tiles_y, tiles;  // per image
+    int tiles_x, tiles_y, tiles;     // per image, forward/binning tiles (TILE_W x TILE_H)
+    int btiles_x, btiles_y, btiles;  // per image, backward tiles (8 x 8)
 };
 
 inline Dims make_dims(int B, int H, int W, int C, int V, int F)
 {
     Dims d;
     d.B = B; d.H = H; d.W = W; d.C = C; d.V = V; d.F = F;
-    d.tiles_x = (W + TILE - 1) / TILE;
-    d.tiles_y = (H + TILE - 1) / TILE;
+    d.tiles_x = (W + TILE_W - 1) / TILE_W;
+    d.tiles_y = (H + TILE_H - 1) / TILE_H;
     d.tiles = d.tiles_x * d.tiles_y;
+    d.btiles_x = (W + 7) / 8;
+    d.btiles_y = (H + 7) / 8;
+    d.btiles = d.btiles_x * d.btiles_y;
     return d;
 }
 

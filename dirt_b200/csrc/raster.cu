@@ -1,14 +1,21 @@
-// raster.cu -- forward rasteriser: one warp per 8x8 screen tile, z-buffer in registers.
+// raster.cu -- forward rasteriser: one warp per 16x8 screen tile, a 2x2 pixel quad per lane,
+// z-buffer in registers.
 //
 // Replaces the GL draw loop + upload_background/download_pixels of the reference
 // (csrc/rasterise_egl.cpp:349-396, csrc/rasterise_egl.cu:10-38,65-91): the background is read
 // and the output written directly in the [B,H,W,C] tensors, top row first.
 //
-// Per tile: the tile's binned face list and the image's large-face list are consumed in chunks
-// of 32 (one face per lane: load the 64-B coverage record, move the edge functions to the tile
-// origin in int64, reject faces that cannot touch the tile), survivors are parked in shared
-// memory and broadcast one at a time to all lanes, each lane testing its two pixels (S5, S7).
-// The winner is min (depth key, face index) -- order independent, so list order does not matter.
+// Per tile, the binned face list (KIND_SMALL faces, int32 arithmetic only) and the image's large
+// list (KIND_LARGE: int64 tile-origin move; KIND_HARD: homogeneous fp64) are consumed in chunks of 32:
+//   lane phase  : one face per lane -- load its 64-B coverage record, move the three edge functions
+//                 to the tile origin, reject faces whose edge functions are negative on the whole
+//                 tile, bound the face's nearest depth key over the tile, park survivors in shared
+//                 memory;
+//   warp phase  : survivors are taken nearest-first (REDUX.MIN over the bounds) and broadcast to all
+//                 lanes, each lane testing its four pixels (S5, S7); the loop stops as soon as the
+//                 nearest remaining bound is farther than every pixel already covered.
+// The visible face of a pixel is min (depth key, face index) -- order independent, so neither the list
+// order nor the early exit can change the result.
 #include "common.cuh"
 
 namespace dirt {
@@ -24,10 +31,15 @@ struct __align__(16) Slot {
 };
 static_assert(sizeof(Slot) == 64, "Slot must be 64 bytes");
 
-struct PixelPair {
-    uint32_t key0, key1;
-    int32_t face0, face1;
+// best (depth key, face) of the lane's four pixels, packed key<<32 | face so one unsigned compare orders both
+struct Quad {
+    unsigned long long best[4];   // [0]=(row0,col0) [1]=(row0,col1) [2]=(row1,col0) [3]=(row1,col1)
 };
+
+__device__ __forceinline__ unsigned long long pack(uint32_t key, int32_t face)
+{
+    return ((unsigned long long)key << 32) | (uint32_t)face;
+}
 
 __device__ __forceinline__ int32_t clamp_q(int64_t q)
 {
@@ -35,109 +47,177 @@ __device__ __forceinline__ int32_t clamp_q(int64_t q)
     return (int32_t)(q > lim ? lim : (q < -lim ? -lim : q));
 }
 
-// hard faces (H1-H3): homogeneous double-precision evaluation at this lane's two pixels
-__device__ __noinline__ void hard_face_pixels(const float* __restrict__ verts, const TriInterp* __restrict__ itp_b,
-                                              int face, int H, int W, int col, int row0, bool& in0, bool& in1,
-                                              uint32_t& key0, uint32_t& key1)
+// hard faces (H1-H3): homogeneous double-precision evaluation at this lane's four pixels.
+// Returns the depth keys (0xFFFFFFFF where the pixel is not covered).
+__device__ __noinline__ uint4 hard_face_keys(const float* __restrict__ verts, const TriInterp* __restrict__ itp_b,
+                                             int face, int H, int W, int col0, int row0)
 {
-    const TriInterp t = load_interp(itp_b + face);
+    const int4 ids = __ldg(reinterpret_cast<const int4*>(itp_b + face) + 2);   // {sC, v0, v1, v2}
     float p[3][4];
-    const int vid[3] = {t.v0, t.v1, t.v2};
+    const int vid[3] = {ids.y, ids.z, ids.w};
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
         const float4 v = __ldg(reinterpret_cast<const float4*>(verts) + vid[k]);
         p[k][0] = v.x; p[k][1] = v.y; p[k][2] = v.z; p[k][3] = v.w;
     }
     double gq[3][3], gs[3], gz[3];
-    in0 = in1 = false;
-    key0 = key1 = KEY_EMPTY;
-    if (!exact::planes_double(p, H, W, gq, gs, gz)) return;
+    uint32_t keys[4] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu};
+    if (exact::planes_double(p, H, W, gq, gs, gz)) {
 #pragma unroll
-    for (int pix = 0; pix < 2; ++pix) {
-        const int row = row0 + pix;
-        bool in = true;
-        double qv[3];
+        for (int pix = 0; pix < 4; ++pix) {
+            const int row = row0 + (pix >> 1), col = col0 + (pix & 1);
+            bool in = true;
+            double qv[3];
 #pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            const double v = exact::plane_double(gq[k], col, row);
-            qv[k] = v;
-            const bool own = gq[k][0] > 0.0 || (gq[k][0] == 0.0 && gq[k][1] > 0.0);
-            if (!(v > 0.0 || (v == 0.0 && own))) in = false;
+            for (int k = 0; k < 3; ++k) {
+                const double v = exact::plane_double(gq[k], col, row);
+                qv[k] = v;
+                const bool own = gq[k][0] > 0.0 || (gq[k][0] == 0.0 && gq[k][1] > 0.0);
+                if (!(v > 0.0 || (v == 0.0 && own))) in = false;
+            }
+            const double sum = __dadd_rn(__dadd_rn(qv[0], qv[1]), qv[2]);
+            in = in && (sum > 0.0);
+            const float z = (float)exact::plane_double(gz, col, row);
+            if (in) keys[pix] = exact::depth_key(z);
         }
-        const double sum = __dadd_rn(__dadd_rn(qv[0], qv[1]), qv[2]);
-        in = in && (sum > 0.0);
-        const float z = (float)exact::plane_double(gz, col, row);
-        const uint32_t key = exact::depth_key(z);
-        if (pix == 0) { in0 = in; key0 = key; } else { in1 = in; key1 = key; }
     }
+    return make_uint4(keys[0], keys[1], keys[2], keys[3]);
 }
 
-// Consume one face list for this warp's tile.
+// Consume one face list for this warp's tile.  SMALL: the list holds KIND_SMALL faces only.
+template <bool SMALL>
 __device__ __forceinline__ void consume_list(const int* __restrict__ list, int count, const TriCov* __restrict__ cov_b,
                                              const TriInterp* __restrict__ itp_b, const float* __restrict__ verts,
-                                             Slot* slots, int lane, int tcol0, int trow0, int H, int W,
-                                             PixelPair& best)
+                                             Slot* slots, int lane, int tcol0, int trow0, int H, int W, Quad& quad,
+                                             uint32_t& tile_max)
 {
-    const int dx = lane & 7, dy = (lane >> 3) * 2;
-    const int col = tcol0 + dx, row0 = trow0 + dy;
-    const float colf = (float)col, row0f = (float)row0, row1f = (float)(row0 + 1);
+    const int dx = (lane & 7) * 2, dy = (lane >> 3) * 2;
+    const int col0 = tcol0 + dx, row0 = trow0 + dy;
+    const float c0f = (float)col0, c1f = (float)(col0 + 1), r0f = (float)row0, r1f = (float)(row0 + 1);
+    const float tc0 = (float)tcol0, tc1 = (float)(tcol0 + TILE_W - 1), tr0 = (float)trow0, tr1 = (float)(trow0 + TILE_H - 1);
+
     for (int base = 0; base < count; base += 32) {
         const int i = base + lane;
         const int f = (i < count) ? __ldg(&list[i]) : -1;
-        bool alive = false;
+        uint32_t order = 0xFFFFFFFFu;   // (nearest possible depth key << 5) | lane; 0xFFFFFFFF: not a candidate
         if (f >= 0) {
             const TriCov c = load_cov(cov_b + f);
             Slot s;
-            s.face = f; s.kind = (int32_t)c.kind; s.pad0 = s.pad1 = 0;
+            s.face = f; s.kind = (int32_t)c.s.kind; s.pad0 = s.pad1 = 0;
             s.A0 = c.A0; s.B0 = c.B0; s.A1 = c.A1; s.B1 = c.B1; s.A2 = c.A2; s.B2 = c.B2;
-            s.zA = c.zA; s.zB = c.zB; s.zC = c.zC;
-            if (c.kind == 1u) {
-                const int64_t Q0 = c.q0 + (int64_t)c.A0 * tcol0 + (int64_t)c.B0 * trow0;
-                const int64_t Q1 = c.q1 + (int64_t)c.A1 * tcol0 + (int64_t)c.B1 * trow0;
-                const int64_t Q2 = c.q2 + (int64_t)c.A2 * tcol0 + (int64_t)c.B2 * trow0;
-                // the largest value each edge function takes on the tile's 8x8 pixel centres
-                const int64_t m0 = Q0 + max(0, 7 * c.A0) + max(0, 7 * c.B0);
-                const int64_t m1 = Q1 + max(0, 7 * c.A1) + max(0, 7 * c.B1);
-                const int64_t m2 = Q2 + max(0, 7 * c.A2) + max(0, 7 * c.B2);
+            bool alive = false;
+            float zA, zB, zC;
+            if (SMALL || c.s.kind == KIND_SMALL) {
+                const int oc = tcol0 - c.s.cref, orow = trow0 - c.s.rref;
+                s.Q0 = c.s.q0r + c.A0 * oc + c.B0 * orow;
+                s.Q1 = c.s.q1r + c.A1 * oc + c.B1 * orow;
+                s.Q2 = c.s.q2r + c.A2 * oc + c.B2 * orow;
+                zA = c.s.zA; zB = c.s.zB; zC = c.s.zC;
+                // the largest value each edge function takes on the tile's pixel centres
+                const int m0 = s.Q0 + max(0, (TILE_W - 1) * c.A0) + max(0, (TILE_H - 1) * c.B0);
+                const int m1 = s.Q1 + max(0, (TILE_W - 1) * c.A1) + max(0, (TILE_H - 1) * c.B1);
+                const int m2 = s.Q2 + max(0, (TILE_W - 1) * c.A2) + max(0, (TILE_H - 1) * c.B2);
+                alive = (m0 | m1 | m2) >= 0;
+            } else if (c.s.kind == KIND_LARGE) {
+                const int64_t Q0 = c.l.q0 + (int64_t)c.A0 * tcol0 + (int64_t)c.B0 * trow0;
+                const int64_t Q1 = c.l.q1 + (int64_t)c.A1 * tcol0 + (int64_t)c.B1 * trow0;
+                const int64_t Q2 = c.l.q2 + (int64_t)c.A2 * tcol0 + (int64_t)c.B2 * trow0;
+                const int64_t m0 = Q0 + max(0, (TILE_W - 1) * c.A0) + max(0, (TILE_H - 1) * c.B0);
+                const int64_t m1 = Q1 + max(0, (TILE_W - 1) * c.A1) + max(0, (TILE_H - 1) * c.B1);
+                const int64_t m2 = Q2 + max(0, (TILE_W - 1) * c.A2) + max(0, (TILE_H - 1) * c.B2);
                 alive = (m0 >= 0) && (m1 >= 0) && (m2 >= 0);
+                // clamping keeps every sign: |A*dx + B*dy| < 2^29 inside a tile
                 s.Q0 = clamp_q(Q0); s.Q1 = clamp_q(Q1); s.Q2 = clamp_q(Q2);
-            } else if (c.kind == 2u) {
-                alive = true;
+                zA = c.l.zA; zB = c.l.zB; zC = c.l.zC;
+            } else {   // KIND_HARD
+                alive = c.s.kind == KIND_HARD;
                 s.Q0 = s.Q1 = s.Q2 = 0;
+                zA = zB = zC = 0.f;
             }
+            s.zA = zA; s.zB = zB; s.zC = zC;
             if (alive) {
+                uint32_t kmin = 0;
+                if (c.s.kind != KIND_HARD) {
+                    // the rounded depth is monotone in col and in row, so its minimum over the tile is at a corner
+                    const float z00 = exact::depth_normal(zA, zB, zC, tc0, tr0), z01 = exact::depth_normal(zA, zB, zC, tc1, tr0);
+                    const float z10 = exact::depth_normal(zA, zB, zC, tc0, tr1), z11 = exact::depth_normal(zA, zB, zC, tc1, tr1);
+                    const float zmin = fminf(fminf(z00, z01), fminf(z10, z11));
+                    kmin = (zmin >= 0.f) ? min(exact::depth_key(zmin), KEY_EMPTY) : 0u;   // NaN -> 0 (conservative)
+                }
+                order = (kmin << 5) | (uint32_t)lane;
                 uint4* dst = reinterpret_cast<uint4*>(&slots[lane]);
                 const uint4* src = reinterpret_cast<const uint4*>(&s);
                 dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2]; dst[3] = src[3];
             }
         }
-        unsigned mask = __ballot_sync(0xffffffffu, alive);
         __syncwarp();
-        while (mask) {
-            const int j = __ffs(mask) - 1;
-            mask &= mask - 1;
+        while (true) {
+            const uint32_t nearest = __reduce_min_sync(0xffffffffu, order);
+            // strict: a face whose nearest key ties the farthest covered pixel could still win on face index
+            if (nearest == 0xFFFFFFFFu || (nearest >> 5) > tile_max) break;
+            const int j = nearest & 31;
+            if (lane == j) order = 0xFFFFFFFFu;
             const Slot s = slots[j];
-            bool in0, in1;
-            uint32_t key0, key1;
-            if (s.kind == 1) {
-                const int32_t n0 = s.Q0 + s.A0 * dx + s.B0 * dy;
-                const int32_t n1 = s.Q1 + s.A1 * dx + s.B1 * dy;
-                const int32_t n2 = s.Q2 + s.A2 * dx + s.B2 * dy;
-                in0 = (n0 | n1 | n2) >= 0;
-                in1 = ((n0 + s.B0) | (n1 + s.B1) | (n2 + s.B2)) >= 0;
-                key0 = exact::depth_key(exact::depth_normal(s.zA, s.zB, s.zC, colf, row0f));
-                key1 = exact::depth_key(exact::depth_normal(s.zA, s.zB, s.zC, colf, row1f));
+            uint32_t k00, k01, k10, k11;
+            if (SMALL || s.kind != (int32_t)KIND_HARD) {
+                const int32_t a0 = s.Q0 + s.A0 * dx + s.B0 * dy, a1 = s.Q1 + s.A1 * dx + s.B1 * dy, a2 = s.Q2 + s.A2 * dx + s.B2 * dy;
+                const bool in00 = (a0 | a1 | a2) >= 0;
+                const bool in01 = ((a0 + s.A0) | (a1 + s.A1) | (a2 + s.A2)) >= 0;
+                const int32_t b0 = a0 + s.B0, b1 = a1 + s.B1, b2 = a2 + s.B2;
+                const bool in10 = (b0 | b1 | b2) >= 0;
+                const bool in11 = ((b0 + s.A0) | (b1 + s.A1) | (b2 + s.A2)) >= 0;
+                const float zr0 = __fmaf_rn(s.zB, r0f, s.zC), zr1 = __fmaf_rn(s.zB, r1f, s.zC);
+                k00 = in00 ? exact::depth_key(__fmaf_rn(s.zA, c0f, zr0)) : 0xFFFFFFFFu;
+                k01 = in01 ? exact::depth_key(__fmaf_rn(s.zA, c1f, zr0)) : 0xFFFFFFFFu;
+                k10 = in10 ? exact::depth_key(__fmaf_rn(s.zA, c0f, zr1)) : 0xFFFFFFFFu;
+                k11 = in11 ? exact::depth_key(__fmaf_rn(s.zA, c1f, zr1)) : 0xFFFFFFFFu;
             } else {
-                hard_face_pixels(verts, itp_b, s.face, H, W, col, row0, in0, in1, key0, key1);
+                const uint4 k = hard_face_keys(verts, itp_b, s.face, H, W, col0, row0);
+                k00 = k.x; k01 = k.y; k10 = k.z; k11 = k.w;
             }
-            if (in0 && (key0 < best.key0 || (key0 == best.key0 && s.face < best.face0))) {
-                best.key0 = key0; best.face0 = s.face;
-            }
-            if (in1 && (key1 < best.key1 || (key1 == best.key1 && s.face < best.face1))) {
-                best.key1 = key1; best.face1 = s.face;
-            }
+            const unsigned long long p00 = pack(k00, s.face), p01 = pack(k01, s.face);
+            const unsigned long long p10 = pack(k10, s.face), p11 = pack(k11, s.face);
+            if (p00 < quad.best[0]) quad.best[0] = p00;
+            if (p01 < quad.best[1]) quad.best[1] = p01;
+            if (p10 < quad.best[2]) quad.best[2] = p10;
+            if (p11 < quad.best[3]) quad.best[3] = p11;
+            const uint32_t far = max(max((uint32_t)(quad.best[0] >> 32), (uint32_t)(quad.best[1] >> 32)),
+                                     max((uint32_t)(quad.best[2] >> 32), (uint32_t)(quad.best[3] >> 32)));
+            tile_max = __reduce_max_sync(0xffffffffu, far);
         }
         __syncwarp();
+    }
+}
+
+template <int CT>
+__device__ __forceinline__ void shade_pixel(const TriInterp& ti, int col, int row, const float* __restrict__ cols,
+                                            float* __restrict__ out, int C)
+{
+    // perspective-correct interpolation c2 + b0*(c0-c2) + b1*(c1-c2): exact for equal vertex colours
+    // (tests/square_test.py).  Values only, no decision depends on them.
+    const float dc = (float)(col - ti.cref), dr = (float)(row - ti.rref);
+    const float S = fmaf(ti.sA, dc, fmaf(ti.sB, dr, ti.sC));
+    const float cw = __frcp_rn(S);
+    const float b0 = fmaf(ti.q0A, dc, fmaf(ti.q0B, dr, ti.q0C)) * cw;
+    const float b1 = fmaf(ti.q1A, dc, fmaf(ti.q1B, dr, ti.q1C)) * cw;
+    if (CT == 4) {
+        const float4 c0 = __ldg(reinterpret_cast<const float4*>(cols) + ti.v0);
+        const float4 c1 = __ldg(reinterpret_cast<const float4*>(cols) + ti.v1);
+        const float4 c2 = __ldg(reinterpret_cast<const float4*>(cols) + ti.v2);
+        float4 o;
+        o.x = fmaf(b0, c0.x - c2.x, fmaf(b1, c1.x - c2.x, c2.x));
+        o.y = fmaf(b0, c0.y - c2.y, fmaf(b1, c1.y - c2.y, c2.y));
+        o.z = fmaf(b0, c0.z - c2.z, fmaf(b1, c1.z - c2.z, c2.z));
+        o.w = fmaf(b0, c0.w - c2.w, fmaf(b1, c1.w - c2.w, c2.w));
+        *reinterpret_cast<float4*>(out) = o;
+    } else {
+        const float* c0 = cols + (size_t)ti.v0 * C;
+        const float* c1 = cols + (size_t)ti.v1 * C;
+        const float* c2 = cols + (size_t)ti.v2 * C;
+        for (int ch = 0; ch < C; ++ch) {
+            const float a2 = __ldg(&c2[ch]);
+            out[ch] = fmaf(b0, __ldg(&c0[ch]) - a2, fmaf(b1, __ldg(&c1[ch]) - a2, a2));
+        }
     }
 }
 
@@ -150,78 +230,60 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) raster_kernel(
 {
     __shared__ Slot slots_all[WARPS_PER_BLOCK][32];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const long long tile_global = (long long)blockIdx.x * WARPS_PER_BLOCK + warp;
-    if (tile_global >= (long long)d.B * d.tiles) return;
-    const int b = (int)(tile_global / d.tiles);
-    const int t = (int)(tile_global - (long long)b * d.tiles);
+    const int t = blockIdx.x * WARPS_PER_BLOCK + warp;
+    if (t >= d.tiles) return;
+    for (int b = blockIdx.y; b < d.B; b += gridDim.y) {   // gridDim.y == B unless B exceeds the grid limit
     const int ty = t / d.tiles_x, tx = t - ty * d.tiles_x;
-    const int tcol0 = tx * TILE, trow0 = ty * TILE;
+    const int tcol0 = tx * TILE_W, trow0 = ty * TILE_H;
 
     const TriCov* cov_b = ws.cov + (size_t)b * d.F;
     const TriInterp* itp_b = ws.itp + (size_t)b * d.F;
     const float* verts = vertices + (size_t)b * d.V * 4;
 
-    PixelPair best;
-    best.key0 = best.key1 = KEY_EMPTY;
-    best.face0 = best.face1 = -1;
-
-    const int2 range = ws.tile_range[tile_global];
-    consume_list(ws.refs + range.x, range.y, cov_b, itp_b, verts, slots_all[warp], lane, tcol0, trow0, d.H, d.W, best);
-    const int nlarge = ws.large_count[b];
-    if (nlarge > 0)
-        consume_list(ws.large_list + (size_t)b * d.F, nlarge, cov_b, itp_b, verts, slots_all[warp], lane, tcol0, trow0,
-                     d.H, d.W, best);
-
-    const int col = tcol0 + (lane & 7), row0 = trow0 + (lane >> 3) * 2;
-    if (col >= d.W) return;
+    Quad quad;
 #pragma unroll
-    for (int pix = 0; pix < 2; ++pix) {
-        const int row = row0 + pix;
-        if (row >= d.H) break;
-        const int face = pix ? best.face1 : best.face0;
+    for (int i = 0; i < 4; ++i) quad.best[i] = pack(KEY_EMPTY, 0);
+    uint32_t tile_max = KEY_EMPTY;
+
+    const int2 range = ws.tile_range[(size_t)b * d.tiles + t];
+    const int nlarge = ws.large_count[b];
+    if (range.y > 0)
+        consume_list<true>(ws.refs + range.x, range.y, cov_b, itp_b, verts, slots_all[warp], lane, tcol0, trow0, d.H, d.W,
+                           quad, tile_max);
+    if (nlarge > 0)
+        consume_list<false>(ws.large_list + (size_t)b * d.F, nlarge, cov_b, itp_b, verts, slots_all[warp], lane, tcol0,
+                            trow0, d.H, d.W, quad, tile_max);
+
+    const int col0 = tcol0 + (lane & 7) * 2, row0 = trow0 + (lane >> 3) * 2;
+    const int C = (CT > 0) ? CT : d.C;
+    const float* cols = vertex_colors + (size_t)b * d.V * C;
+    int prev_face = -1;
+    TriInterp ti;
+#pragma unroll
+    for (int pix = 0; pix < 4; ++pix) {
+        const int row = row0 + (pix >> 1), col = col0 + (pix & 1);
+        if (row >= d.H || col >= d.W) continue;
+        const bool covered = (uint32_t)(quad.best[pix] >> 32) < KEY_EMPTY;
+        const int face = covered ? (int)(uint32_t)quad.best[pix] : -1;
         const size_t p = ((size_t)b * d.H + row) * d.W + col;
+        if (face_ids_out) face_ids_out[p] = face;
         if (MODE == 1) {
-            if (face_ids_out) face_ids_out[p] = face;
             if (gbuffer_out) {
                 float4 g = make_float4(-1.f, -1.f, -1.f, __int_as_float(0x7f800000));
                 if (face >= 0) g = exact::gbuffer_at(load_interp(itp_b + face), col, row);
                 reinterpret_cast<float4*>(gbuffer_out)[p] = g;
             }
-        } else {
-            if (face_ids_out) face_ids_out[p] = face;
-            const int C = (CT > 0) ? CT : d.C;
-            if (face < 0) {
-                if (CT == 4) {
-                    reinterpret_cast<float4*>(pixels)[p] = __ldg(reinterpret_cast<const float4*>(background) + p);
-                } else {
-                    for (int ch = 0; ch < C; ++ch) pixels[p * C + ch] = __ldg(&background[p * C + ch]);
-                }
+        } else if (face < 0) {
+            if (CT == 4) {
+                reinterpret_cast<float4*>(pixels)[p] = __ldg(reinterpret_cast<const float4*>(background) + p);
             } else {
-                const TriInterp ti = load_interp(itp_b + face);
-                const float4 g = exact::gbuffer_at(ti, col, row);
-                const float* cols = vertex_colors + (size_t)b * d.V * C;
-                if (CT == 4) {
-                    const float4 c0 = __ldg(reinterpret_cast<const float4*>(cols) + ti.v0);
-                    const float4 c1 = __ldg(reinterpret_cast<const float4*>(cols) + ti.v1);
-                    const float4 c2 = __ldg(reinterpret_cast<const float4*>(cols) + ti.v2);
-                    // c2 + b0*(c0-c2) + b1*(c1-c2): exact for equal vertex colours (tests/square_test.py)
-                    float4 o;
-                    o.x = fmaf(g.x, c0.x - c2.x, fmaf(g.y, c1.x - c2.x, c2.x));
-                    o.y = fmaf(g.x, c0.y - c2.y, fmaf(g.y, c1.y - c2.y, c2.y));
-                    o.z = fmaf(g.x, c0.z - c2.z, fmaf(g.y, c1.z - c2.z, c2.z));
-                    o.w = fmaf(g.x, c0.w - c2.w, fmaf(g.y, c1.w - c2.w, c2.w));
-                    reinterpret_cast<float4*>(pixels)[p] = o;
-                } else {
-                    const float* c0 = cols + (size_t)ti.v0 * C;
-                    const float* c1 = cols + (size_t)ti.v1 * C;
-                    const float* c2 = cols + (size_t)ti.v2 * C;
-                    for (int ch = 0; ch < C; ++ch) {
-                        const float a2 = __ldg(&c2[ch]);
-                        pixels[p * C + ch] = fmaf(g.x, __ldg(&c0[ch]) - a2, fmaf(g.y, __ldg(&c1[ch]) - a2, a2));
-                    }
-                }
+                for (int ch = 0; ch < C; ++ch) pixels[p * C + ch] = __ldg(&background[p * C + ch]);
             }
+        } else {
+            if (face != prev_face) { ti = load_interp(itp_b + face); prev_face = face; }
+            shade_pixel<CT>(ti, col, row, cols, pixels + p * C, C);
         }
+    }
     }
 }
 
@@ -229,19 +291,17 @@ cudaError_t launch_raster_forward(const float* vertices, const float* background
                                   int32_t* face_ids_out, const Workspace& ws, const Dims& d, cudaStream_t stream,
                                   int* launches)
 {
-    const long long total_tiles = (long long)d.B * d.tiles;
-    if (total_tiles == 0) return cudaSuccess;
-    const unsigned grid = (unsigned)((total_tiles + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK);
-    const float* v = vertices;
+    if ((long long)d.B * d.tiles == 0) return cudaSuccess;
+    const dim3 grid((unsigned)((d.tiles + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK), (unsigned)min(d.B, 65535));
     ScopedKernelTimer timer(1, stream);
     const bool vec4 = d.C == 4 && ((uintptr_t)background % 16 == 0) && ((uintptr_t)pixels % 16 == 0) &&
                       ((uintptr_t)vertex_colors % 16 == 0);
     if (vec4)
-        raster_kernel<0, 4><<<grid, WARPS_PER_BLOCK * 32, 0, stream>>>(v, background, vertex_colors, pixels, face_ids_out,
-                                                                       nullptr, ws, d);
+        raster_kernel<0, 4><<<grid, WARPS_PER_BLOCK * 32, 0, stream>>>(vertices, background, vertex_colors, pixels,
+                                                                       face_ids_out, nullptr, ws, d);
     else
-        raster_kernel<0, 0><<<grid, WARPS_PER_BLOCK * 32, 0, stream>>>(v, background, vertex_colors, pixels, face_ids_out,
-                                                                       nullptr, ws, d);
+        raster_kernel<0, 0><<<grid, WARPS_PER_BLOCK * 32, 0, stream>>>(vertices, background, vertex_colors, pixels,
+                                                                       face_ids_out, nullptr, ws, d);
     ++*launches;
     return cudaGetLastError();
 }
@@ -249,11 +309,9 @@ cudaError_t launch_raster_forward(const float* vertices, const float* background
 cudaError_t launch_raster_visibility(const float* vertices, int32_t* face_ids, float* gbuffer, const Workspace& ws, const Dims& d,
                                      cudaStream_t stream, int* launches)
 {
-    const long long total_tiles = (long long)d.B * d.tiles;
-    if (total_tiles == 0) return cudaSuccess;
-    const unsigned grid = (unsigned)((total_tiles + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK);
-    raster_kernel<1, 0><<<grid, WARPS_PER_BLOCK * 32, 0, stream>>>(vertices, nullptr, nullptr, nullptr,
-                                                                   face_ids, gbuffer, ws, d);
+    if ((long long)d.B * d.tiles == 0) return cudaSuccess;
+    const dim3 grid((unsigned)((d.tiles + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK), (unsigned)min(d.B, 65535));
+    raster_kernel<1, 0><<<grid, WARPS_PER_BLOCK * 32, 0, stream>>>(vertices, nullptr, nullptr, nullptr, face_ids, gbuffer, ws, d);
     ++*launches;
     return cudaGetLastError();
 }

@@ -31,9 +31,9 @@ __global__ void __launch_bounds__(256) setup_kernel(const float* __restrict__ ve
     TriCov cov;
     TriInterp itp;
     cov.A0 = cov.B0 = cov.A1 = cov.B1 = cov.A2 = cov.B2 = 0;
-    cov.q0 = cov.q1 = cov.q2 = -1;
-    cov.zA = cov.zB = cov.zC = 0.f;
-    cov.kind = 0;
+    cov.l.q0 = cov.l.q1 = cov.l.q2 = -1;
+    cov.l.zA = cov.l.zB = cov.l.zC = 0.f;
+    cov.s.kind = KIND_CULLED;
     itp.q0A = itp.q0B = itp.q0C = itp.q1A = itp.q1B = itp.q1C = itp.sA = itp.sB = 0.f;
     itp.sC = 1.f;
     itp.v0 = itp.v1 = itp.v2 = 0;
@@ -59,6 +59,8 @@ __global__ void __launch_bounds__(256) setup_kernel(const float* __restrict__ ve
         }
     }
     int cmin = 0, cmax = -1, rmin = 0, rmax = -1;
+    int64_t q_abs[3] = {-1, -1, -1};
+    float zpl[3] = {0.f, 0.f, 0.f};
     if (ok) {
         bool hard = false;
         int n_behind = 0;
@@ -116,9 +118,8 @@ __global__ void __launch_bounds__(256) setup_kernel(const float* __restrict__ ve
                     if (cmin > cmax || rmin > rmax) ok = false;
                     else {
                         kind = 1;
-                        cov.A0 = A[0]; cov.B0 = Bc[0]; cov.q0 = q[0];
-                        cov.A1 = A[1]; cov.B1 = Bc[1]; cov.q1 = q[1];
-                        cov.A2 = A[2]; cov.B2 = Bc[2]; cov.q2 = q[2];
+                        cov.A0 = A[0]; cov.B0 = Bc[0]; cov.A1 = A[1]; cov.B1 = Bc[1]; cov.A2 = A[2]; cov.B2 = Bc[2];
+                        q_abs[0] = q[0]; q_abs[1] = q[1]; q_abs[2] = q[2];
                     }
                 }
             }
@@ -126,8 +127,7 @@ __global__ void __launch_bounds__(256) setup_kernel(const float* __restrict__ ve
         if (ok) {
             const int cref = (kind == 1) ? cmin : 0, rref = (kind == 1) ? rmin : 0;
             const double cr = (double)cref, rr = (double)rref;
-            cov.zA = (float)gz[0]; cov.zB = (float)gz[1]; cov.zC = (float)gz[2];
-            cov.kind = (uint32_t)kind;
+            zpl[0] = (float)gz[0]; zpl[1] = (float)gz[1]; zpl[2] = (float)gz[2];
             itp.q0A = (float)gq[0][0]; itp.q0B = (float)gq[0][1];
             itp.q0C = (float)__dadd_rn(__dadd_rn(__dmul_rn(gq[0][0], cr), __dmul_rn(gq[0][1], rr)), gq[0][2]);
             itp.q1A = (float)gq[1][0]; itp.q1B = (float)gq[1][1];
@@ -138,7 +138,35 @@ __global__ void __launch_bounds__(256) setup_kernel(const float* __restrict__ ve
             itp.cref = cref; itp.rref = rref;
         }
     }
-    if (!ok) { kind = 0; cov.kind = 0; }
+    if (!ok) kind = 0;
+
+    // tile bounding box and the layout of the coverage record
+    int tx0 = 0, tx1 = -1, ty0 = 0, ty1 = -1;
+    bool small = false;
+    if (kind != 0) {
+        tx0 = cmin >> TILE_W_SHIFT; tx1 = cmax >> TILE_W_SHIFT;
+        ty0 = rmin >> TILE_H_SHIFT; ty1 = rmax >> TILE_H_SHIFT;
+        // "small" faces are binned per tile and rasterised entirely in int32: that needs a bounded tile count AND bounded
+        // edge coefficients (a huge, mostly off-screen face can have a small clamped bbox): |A|,|B| < 2^18, |q_rel| < 2^29
+        // keep q_rel + A*dcol + B*drow (|dcol|,|drow| < 2^9 inside the binned tiles) below 2^31.
+        const int64_t q0r = q_abs[0] + (int64_t)cov.A0 * cmin + (int64_t)cov.B0 * rmin;
+        const int64_t q1r = q_abs[1] + (int64_t)cov.A1 * cmin + (int64_t)cov.B1 * rmin;
+        const int64_t q2r = q_abs[2] + (int64_t)cov.A2 * cmin + (int64_t)cov.B2 * rmin;
+        const int32_t cmax_abs = max(max(max(abs(cov.A0), abs(cov.B0)), max(abs(cov.A1), abs(cov.B1))), max(abs(cov.A2), abs(cov.B2)));
+        const int64_t qlim = (int64_t)1 << 29;
+        small = kind == 1 && (tx1 - tx0 + 1) * (ty1 - ty0 + 1) <= SMALL_TILE_LIMIT && cmax_abs < (1 << 18) &&
+                q0r > -qlim && q0r < qlim && q1r > -qlim && q1r < qlim && q2r > -qlim && q2r < qlim;
+        if (small) {
+            cov.s.kind = KIND_SMALL;
+            cov.s.q0r = (int32_t)q0r; cov.s.q1r = (int32_t)q1r; cov.s.q2r = (int32_t)q2r;
+            cov.s.zA = zpl[0]; cov.s.zB = zpl[1]; cov.s.zC = zpl[2];
+            cov.s.cref = cmin; cov.s.rref = rmin; cov.s.pad = 0;
+        } else {
+            cov.s.kind = (kind == 2) ? KIND_HARD : KIND_LARGE;
+            cov.l.q0 = q_abs[0]; cov.l.q1 = q_abs[1]; cov.l.q2 = q_abs[2];
+            cov.l.zA = zpl[0]; cov.l.zB = zpl[1]; cov.l.zC = zpl[2];
+        }
+    }
 
     // records (64-B stores as 4 x 16 B)
     {
@@ -152,10 +180,7 @@ __global__ void __launch_bounds__(256) setup_kernel(const float* __restrict__ ve
     if (!BIN) return;
 
     if (kind != 0) {
-        const int tx0 = cmin >> TILE_SHIFT, tx1 = cmax >> TILE_SHIFT;
-        const int ty0 = rmin >> TILE_SHIFT, ty1 = rmax >> TILE_SHIFT;
-        const int ntiles = (tx1 - tx0 + 1) * (ty1 - ty0 + 1);
-        if (kind == 1 && ntiles <= SMALL_TILE_LIMIT) {
+        if (small) {
             bin = make_uint2((uint32_t)tx0 | ((uint32_t)ty0 << 16), (uint32_t)tx1 | ((uint32_t)ty1 << 16));
             int* counts = ws.tile_count + (size_t)b * d.tiles;
             for (int ty = ty0; ty <= ty1; ++ty)
