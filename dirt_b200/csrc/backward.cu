@@ -168,18 +168,137 @@ __global__ void __launch_bounds__(BWD_WARPS_PER_BLOCK * 32) backward_generic_ker
 // =================================================================================================
 // Fast path: C in {1,3,4} with the reference's default grouping ({1}, {3}, {3,1}).
 //
-// One warp per 8x8 tile, two vertically adjacent pixels per lane.  Every per-pixel term of
-// assemble_grads is a product  scalar_j * bary_k  destined for vertex k of one face, so the warp
-// (1) computes per pixel the C colour scalars (grad_pixels) keyed by the pixel's own face and the three
-//     position scalars (a, b, c) keyed by the (possibly dilated) face,
-// (2) loops over the distinct faces present in the tile (REDUX.MIN over the keys), and for each face
-//     reduces the 3*(C+3) sums over all 32 lanes with a transposed butterfly: at every shuffle step a
-//     lane keeps half of the sums and hands the other half to its partner, so 21 sums need
-//     11+6+3+2+1 = 23 shuffles instead of 21*5, and every lane ends up owning one finished sum,
-// (3) issues ONE warp-wide RED (one lane per sum) to grad_vertex_colors / grad_vertices.
-// This replaces the reference's one global atomicAdd per pixel per term
-// (csrc/rasterise_grad_egl.cu:139,227-229) -- 21 atomics per covered pixel -- by 21 per (face, tile).
+// One warp per 8x8 tile, two vertically adjacent pixels per lane.
+//  (1) The tile of `pixels` plus its halo (10 rows x 12 columns: one pixel around for the Scharr taps and
+//      two more to the right for the flat-order reads of 1-wide groups) is staged into shared memory with
+//      cp.async, rows/columns clamped to the frame exactly as at() clamps its taps; all taps are then
+//      LDS at constant offsets.  Tiles whose halo crosses the right frame edge read the taps from global
+//      memory instead (there the flat-order reads wrap into the next row).
+//  (2) Every per-pixel term of assemble_grads is a product  scalar * barycentric  destined for vertex k
+//      of one face: C colour scalars (grad_pixels) keyed by the pixel's own face, three position scalars
+//      (a, b, c = dL/d clip x, y, w of the fragment) keyed by the possibly dilated face.
+//  (3) The warp loops over the distinct faces present in the tile (REDUX.MIN over the keys) and reduces the
+//      3*(C+3) sums of each face over its 32 lanes with a transposed butterfly: at every shuffle step a lane
+//      keeps half of the sums and hands the other half to its partner, so 21 sums need 11+6+3+2+1 = 23
+//      shuffles instead of 21*5, and every lane ends up owning one finished sum: ONE warp-wide RED per
+//      (face, tile) instead of the reference's atomicAdd per pixel per term
+//      (csrc/rasterise_grad_egl.cu:139,227-229).
 // =================================================================================================
+
+constexpr int HALO_ROWS = TILE + 2;   // 10
+constexpr int HALO_COLS = TILE + 4;   // 12: col-1 .. col+10
+
+struct PixelTerms {      // everything one pixel contributes (fast path)
+    int key_col;         // own face (-1: uncovered)
+    int key_pos;         // face receiving the position gradient (-1: none)
+    float bc0, bc1, bc2; // undilated barycentrics
+    float bp0, bp1, bp2; // barycentrics used for the position gradient
+};
+
+struct Fragment {   // a face seen at a pixel: G-buffer entry + vertex ids
+    int face;
+    int v0, v1, v2;
+    float4 g;       // bary0, bary1, bary2, clip_w
+};
+
+__device__ __forceinline__ Fragment fragment_at(const TriInterp* __restrict__ itp_b, int face, int col, int row)
+{
+    Fragment fr;
+    fr.face = face;
+    if (face >= 0) {
+        const TriInterp t = load_interp(itp_b + face);
+        fr.v0 = t.v0; fr.v1 = t.v1; fr.v2 = t.v2;
+        fr.g = exact::gbuffer_at(t, col, row);
+    } else {
+        fr.v0 = fr.v1 = fr.v2 = -1;
+        fr.g = make_float4(-1.f, -1.f, -1.f, __int_as_float(0x7f800000));
+    }
+    return fr;
+}
+
+// dilation (csrc/rasterise_grad_egl.cu:155-194): returns the fragment the position gradient goes to
+__device__ __forceinline__ Fragment dilate(const Fragment& own, const float (&sx)[3], const float (&sy)[3],
+                                           const int32_t* __restrict__ ids, const TriInterp* __restrict__ itp_b,
+                                           int col, int row, int H, int W, int& src)
+{
+    src = 0;
+    if (!(col > 0 && row > 0 && col < W - 1 && row < H - 1)) return own;
+    int dx = (l1(sx) > l1(sy)) ? 1 : 0, dy = 1 - dx;  // buffer (y-up) orientation
+    if ((col + row) & 1) { dx = -dx; dy = -dy; }
+#pragma unroll
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        const int nc = col + dx, nr = row - dy;
+        const int fn = __ldg(&ids[nr * W + nc]);
+        if (fn >= 0 && fn != own.face) {
+            const Fragment n = fragment_at(itp_b, fn, nc, nr);
+            const bool differs = (own.face < 0) || n.v0 != own.v0 || n.v1 != own.v1 || n.v2 != own.v2;
+            if (differs && own.g.w > n.g.w) {
+                src = 1 + (dx + 1) + 3 * (dy + 1);   // distinguishes the four neighbours
+                return n;
+            }
+        }
+        dx = -dx; dy = -dy;
+    }
+    return own;
+}
+
+__device__ __forceinline__ void cp_async_16(void* smem, const void* gmem)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_4(void* smem, const void* gmem)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// Scharr sums of the first group (width N0) from the staged tile.  lr/lc: pixel position inside the halo tile.
+template <int C, int N0>
+__device__ __forceinline__ void scharr_smem(const float* __restrict__ tile, int lr, int lc, float (&sx)[3], float (&sy)[3])
+{
+    // comp k of the tap at (lr+dr, lc+dc): channel k (N0 == 3) or channel 0 of the pixel k places to the right (N0 == 1)
+    auto T = [&](int dr, int dc, int k) -> float {
+        return (N0 == 3) ? tile[((lr + dr) * HALO_COLS + lc + dc) * C + k] : tile[((lr + dr) * HALO_COLS + lc + dc + k) * C];
+    };
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        // at(ox,oy) is image (row - oy, col + ox)
+        const float a_mm = T(+1, -1, k), a_mp = T(-1, -1, k), a_pm = T(+1, +1, k), a_pp = T(-1, +1, k);
+        const float a_m0 = T(0, -1, k), a_p0 = T(0, +1, k), a_0m = T(+1, 0, k), a_0p = T(-1, 0, k);
+        sx[k] = scharr_comp(a_mm, a_mp, a_pm, a_pp, a_m0, a_p0);
+        sy[k] = scharr_comp(a_mm, a_pm, a_mp, a_pp, a_0m, a_0p);
+    }
+}
+
+// the 1-wide second group of C == 4 (channel 3): comp k = channel 3 of the pixel k places to the right
+__device__ __forceinline__ void scharr_smem_c4_group1(const float* __restrict__ tile, int lr, int lc, float (&sx)[3], float (&sy)[3])
+{
+    auto T = [&](int dr, int dc, int k) -> float { return tile[((lr + dr) * HALO_COLS + lc + dc + k) * 4 + 3]; };
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const float a_mm = T(+1, -1, k), a_mp = T(-1, -1, k), a_pm = T(+1, +1, k), a_pp = T(-1, +1, k);
+        const float a_m0 = T(0, -1, k), a_p0 = T(0, +1, k), a_0m = T(+1, 0, k), a_0p = T(-1, 0, k);
+        sx[k] = scharr_comp(a_mm, a_mp, a_pm, a_pp, a_m0, a_p0);
+        sy[k] = scharr_comp(a_mm, a_pm, a_mp, a_pp, a_0m, a_0p);
+    }
+}
+
+// global-memory taps (tiles at the right frame edge): three components of group [c0, c0+N0) at the clamped pixel
+template <int C, int N0>
+__device__ __forceinline__ void scharr_global(const float* __restrict__ pixels, int b, int row, int col, const Dims& d,
+                                              int c0, float (&sx)[3], float (&sy)[3])
+{
+    const V3 a_mm = group_at(pixels, b, row + 1, col - 1, d, c0, N0), a_mp = group_at(pixels, b, row - 1, col - 1, d, c0, N0);
+    const V3 a_pm = group_at(pixels, b, row + 1, col + 1, d, c0, N0), a_pp = group_at(pixels, b, row - 1, col + 1, d, c0, N0);
+    const V3 a_m0 = group_at(pixels, b, row, col - 1, d, c0, N0), a_p0 = group_at(pixels, b, row, col + 1, d, c0, N0);
+    const V3 a_0m = group_at(pixels, b, row + 1, col, d, c0, N0), a_0p = group_at(pixels, b, row - 1, col, d, c0, N0);
+    sx[0] = scharr_comp(a_mm.x, a_mp.x, a_pm.x, a_pp.x, a_m0.x, a_p0.x);
+    sx[1] = scharr_comp(a_mm.y, a_mp.y, a_pm.y, a_pp.y, a_m0.y, a_p0.y);
+    sx[2] = scharr_comp(a_mm.z, a_mp.z, a_pm.z, a_pp.z, a_m0.z, a_p0.z);
+    sy[0] = scharr_comp(a_mm.x, a_pm.x, a_mp.x, a_pp.x, a_0m.x, a_0p.x);
+    sy[1] = scharr_comp(a_mm.y, a_pm.y, a_mp.y, a_pp.y, a_0m.y, a_0p.y);
+    sy[2] = scharr_comp(a_mm.z, a_pm.z, a_mp.z, a_pp.z, a_0m.z, a_0p.z);
+}
 
 template <int N>
 struct TransposedReduce {
@@ -215,6 +334,7 @@ __device__ __forceinline__ int transposed_reduce_owner(int lane)
     int sizes[6];
     int n = N, steps = 0;
     for (int bit = 16; bit && n > 1; bit >>= 1) { sizes[steps++] = n; n = (n + 1) / 2; }
+    if (steps == 0) return lane == 0 ? 0 : -1;
     int p = 0;
     bool valid = true;
     for (int s = steps - 1; s >= 0; --s) {
@@ -224,119 +344,9 @@ __device__ __forceinline__ int transposed_reduce_owner(int lane)
         valid = valid && (p < sizes[s]);
     }
     // lanes that differ only in the unused low bits all hold the same (fully reduced) sum: let one write
-    const int used_mask = ~((16 >> (steps - 1)) - 1) & 31;
-    if (steps == 0) return lane == 0 ? 0 : -1;
-    if ((lane & ~used_mask & 31) != 0) valid = false;
+    const int unused = (16 >> (steps - 1)) - 1;
+    if (lane & unused) valid = false;
     return valid ? p : -1;
-}
-
-struct PixelTerms {      // everything one pixel contributes (fast path)
-    int key_col;         // own face (-1: uncovered)
-    int key_pos;         // face receiving the position gradient (-1: none)
-    float bc0, bc1, bc2; // undilated barycentrics
-    float bp0, bp1, bp2; // barycentrics used for the position gradient
-    float a, b, c;       // d(loss)/d(clip x,y,w) of the fragment: coefficients multiplying the barycentrics
-};
-
-template <int C>
-__device__ __forceinline__ void load_pixel(const float* __restrict__ base, size_t pix, float (&out)[C])
-{
-    if (C == 4) {
-        const float4 v = __ldg(reinterpret_cast<const float4*>(base) + pix);
-        out[0] = v.x; out[1] = v.y; out[2] = v.z; out[3 % C] = v.w;
-    } else {
-#pragma unroll
-        for (int ch = 0; ch < C; ++ch) out[ch] = __ldg(base + pix * C + ch);
-    }
-}
-
-// three components of channel group [c0, c0+n) at the clamped pixel (r,c) of image b  (see group_at)
-template <int C, int N0>
-__device__ __forceinline__ V3 tap(const float* __restrict__ pixels, int b, int r, int c, const Dims& d, int c0)
-{
-    r = max(0, min(d.H - 1, r));
-    c = max(0, min(d.W - 1, c));
-    const size_t lin = ((size_t)b * d.H + r) * d.W + c;
-    V3 v;
-    if (N0 == 3) {
-        if (C == 4) {
-            const float4 q = __ldg(reinterpret_cast<const float4*>(pixels) + lin);
-            v.x = q.x; v.y = q.y; v.z = q.z;
-        } else {
-            const float* p = pixels + lin * C + c0;
-            v.x = __ldg(p); v.y = __ldg(p + 1); v.z = __ldg(p + 2);
-        }
-    } else {
-        const size_t total = (size_t)d.B * d.H * d.W;
-        v.x = __ldg(pixels + lin * C + c0);
-        v.y = (lin + 1 < total) ? __ldg(pixels + (lin + 1) * C + c0) : 0.f;
-        v.z = (lin + 2 < total) ? __ldg(pixels + (lin + 2) * C + c0) : 0.f;
-    }
-    return v;
-}
-
-// Scharr sums of one group at pixel (row,col):  sx, sy
-template <int C, int N0>
-__device__ __forceinline__ void scharr_group(const float* __restrict__ pixels, int b, int row, int col, const Dims& d,
-                                             int c0, float (&sx)[3], float (&sy)[3])
-{
-    const V3 a_mm = tap<C, N0>(pixels, b, row + 1, col - 1, d, c0), a_mp = tap<C, N0>(pixels, b, row - 1, col - 1, d, c0);
-    const V3 a_pm = tap<C, N0>(pixels, b, row + 1, col + 1, d, c0), a_pp = tap<C, N0>(pixels, b, row - 1, col + 1, d, c0);
-    const V3 a_m0 = tap<C, N0>(pixels, b, row, col - 1, d, c0), a_p0 = tap<C, N0>(pixels, b, row, col + 1, d, c0);
-    const V3 a_0m = tap<C, N0>(pixels, b, row + 1, col, d, c0), a_0p = tap<C, N0>(pixels, b, row - 1, col, d, c0);
-    sx[0] = scharr_comp(a_mm.x, a_mp.x, a_pm.x, a_pp.x, a_m0.x, a_p0.x);
-    sx[1] = scharr_comp(a_mm.y, a_mp.y, a_pm.y, a_pp.y, a_m0.y, a_p0.y);
-    sx[2] = scharr_comp(a_mm.z, a_mp.z, a_pm.z, a_pp.z, a_m0.z, a_p0.z);
-    sy[0] = scharr_comp(a_mm.x, a_pm.x, a_mp.x, a_pp.x, a_0m.x, a_0p.x);
-    sy[1] = scharr_comp(a_mm.y, a_pm.y, a_mp.y, a_pp.y, a_0m.y, a_0p.y);
-    sy[2] = scharr_comp(a_mm.z, a_pm.z, a_mp.z, a_pp.z, a_0m.z, a_0p.z);
-}
-
-struct Fragment {   // a face seen at a pixel: G-buffer entry + vertex ids
-    int face;
-    int v0, v1, v2;
-    float4 g;       // bary0, bary1, bary2, clip_w
-};
-
-__device__ __forceinline__ Fragment fragment_at(const TriInterp* __restrict__ itp_b, int face, int col, int row)
-{
-    Fragment fr;
-    fr.face = face;
-    if (face >= 0) {
-        const TriInterp t = load_interp(itp_b + face);
-        fr.v0 = t.v0; fr.v1 = t.v1; fr.v2 = t.v2;
-        fr.g = exact::gbuffer_at(t, col, row);
-    } else {
-        fr.v0 = fr.v1 = fr.v2 = -1;
-        fr.g = make_float4(-1.f, -1.f, -1.f, __int_as_float(0x7f800000));
-    }
-    return fr;
-}
-
-// dilation (csrc/rasterise_grad_egl.cu:155-194): returns the fragment the position gradient goes to
-__device__ __forceinline__ Fragment dilate(const Fragment& own, const float (&sx)[3], const float (&sy)[3],
-                                           const int32_t* __restrict__ ids, const TriInterp* __restrict__ itp_b,
-                                           int col, int row, const Dims& d, int& src)
-{
-    src = 0;
-    if (!(col > 0 && row > 0 && col < d.W - 1 && row < d.H - 1)) return own;
-    int dx = (l1(sx) > l1(sy)) ? 1 : 0, dy = 1 - dx;  // buffer (y-up) orientation
-    if ((col + row) & 1) { dx = -dx; dy = -dy; }
-#pragma unroll
-    for (int attempt = 0; attempt < 2; ++attempt) {
-        const int nc = col + dx, nr = row - dy;
-        const int fn = __ldg(&ids[nr * d.W + nc]);
-        if (fn >= 0 && fn != own.face) {
-            const Fragment n = fragment_at(itp_b, fn, nc, nr);
-            const bool differs = (own.face < 0) || n.v0 != own.v0 || n.v1 != own.v1 || n.v2 != own.v2;
-            if (differs && own.g.w > n.g.w) {
-                src = 1 + (dx + 1) + 3 * (dy + 1);   // distinguishes the four neighbours
-                return n;
-            }
-        }
-        dx = -dx; dy = -dy;
-    }
-    return own;
 }
 
 template <int C>
@@ -345,67 +355,117 @@ __global__ void __launch_bounds__(BWD_WARPS_PER_BLOCK * 32) backward_tile_kernel
     const int32_t* __restrict__ face_ids, float* __restrict__ grad_background, float* __restrict__ grad_vertices,
     float* __restrict__ grad_vertex_colors, Workspace ws, Dims d)
 {
-    constexpr int NS = C + 3;        // scalars per pixel: C colour + (a,b,c)
-    constexpr int NV = 3 * NS;       // sums per face
-    constexpr int N0 = (C == 1) ? 1 : 3;   // width of the first group
-    constexpr bool TWO_GROUPS = (C == 4);  // {3,1}
+    constexpr int NS = C + 3;                  // scalars per pixel: C colour + (a,b,c)
+    constexpr int NV = 3 * NS;                 // sums per face
+    constexpr int N0 = (C == 1) ? 1 : 3;       // width of the first group
+    constexpr bool TWO_GROUPS = (C == 4);      // {3,1}
+    constexpr int REACH = (C == 3) ? 1 : 3;    // columns to the right of the pixel that its taps read
+
+    __shared__ __align__(16) float tile_all[BWD_WARPS_PER_BLOCK][HALO_ROWS * HALO_COLS * C];
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const long long tile_global = (long long)blockIdx.x * BWD_WARPS_PER_BLOCK + warp;
-    if (tile_global >= (long long)d.B * d.btiles) return;
-    const int b = (int)(tile_global / d.btiles);
-    const int t = (int)(tile_global - (long long)b * d.btiles);
+    const int t = blockIdx.x * BWD_WARPS_PER_BLOCK + warp;
+    if (t >= d.btiles) return;
     const int ty = t / d.btiles_x, tx = t - ty * d.btiles_x;
-    const int col = tx * TILE + (lane & 7), row0 = ty * TILE + (lane >> 3) * 2;
+    const int tcol0 = tx * TILE, trow0 = ty * TILE;
+    const int lcol = lane & 7, lrow0 = (lane >> 3) * 2;
+    const int col = tcol0 + lcol, row0 = trow0 + lrow0;
+    const int H = d.H, W = d.W;
+    float* tile = tile_all[warp];
 
+    for (int b = blockIdx.y; b < d.B; b += gridDim.y) {
     const TriInterp* itp_b = ws.itp + (size_t)b * d.F;
     const float* verts = vertices + (size_t)b * d.V * 4;
-    const int32_t* ids = face_ids + (size_t)b * d.H * d.W;
+    const int32_t* ids = face_ids + (size_t)b * H * W;
     float* gverts = grad_vertices + (size_t)b * d.V * 4;
     float* gcols = grad_vertex_colors + (size_t)b * d.V * C;
-    const float halfW = 0.5f * (float)d.W, halfH = 0.5f * (float)d.H;
+    const size_t img = (size_t)b * H * W;
+    const float halfW = 0.5f * (float)W, halfH = 0.5f * (float)H;
 
-    PixelTerms term[2];
+    // ---- own faces, grad_pixels, grad_background; does anything reach this tile? --------------------
+    int f_own[2];
     float gp[2][C];
-    bool any_face = false;
+    bool near = false;
+#pragma unroll
+    for (int pix = 0; pix < 2; ++pix) {
+        const int row = row0 + pix;
+        f_own[pix] = -1;
+#pragma unroll
+        for (int ch = 0; ch < C; ++ch) gp[pix][ch] = 0.f;
+        if (col >= W || row >= H) continue;
+        const int pi = row * W + col;
+        const size_t p = img + pi;
+        if (C == 4) {
+            const float4 v = __ldg(reinterpret_cast<const float4*>(grad_pixels) + p);
+            gp[pix][0] = v.x; gp[pix][1 % C] = v.y; gp[pix][2 % C] = v.z; gp[pix][3 % C] = v.w;
+        } else {
+#pragma unroll
+            for (int ch = 0; ch < C; ++ch) gp[pix][ch] = __ldg(grad_pixels + p * C + ch);
+        }
+        const int f = __ldg(&ids[pi]);
+        f_own[pix] = f;
+        // grad_background: grad_pixels where uncovered, 0 elsewhere (:143-148, memset :247)
+        if (C == 4) {
+            reinterpret_cast<float4*>(grad_background)[p] =
+                f < 0 ? make_float4(gp[pix][0], gp[pix][1 % C], gp[pix][2 % C], gp[pix][3 % C]) : make_float4(0.f, 0.f, 0.f, 0.f);
+        } else {
+#pragma unroll
+            for (int ch = 0; ch < C; ++ch) grad_background[p * C + ch] = f < 0 ? gp[pix][ch] : 0.f;
+        }
+        // own coverage, or a covered 4-neighbour that could dilate into this pixel
+        bool n = f >= 0;
+        if (!n && col > 0 && row > 0 && col < W - 1 && row < H - 1)
+            n = __ldg(&ids[pi - 1]) >= 0 || __ldg(&ids[pi + 1]) >= 0 || __ldg(&ids[pi - W]) >= 0 || __ldg(&ids[pi + W]) >= 0;
+        if (!n) f_own[pix] = -2;   // nothing can reach this pixel
+        near = near || n;
+    }
+    if (!__any_sync(0xffffffffu, near)) continue;
+
+    // ---- stage the tile of `pixels` (+halo) ----------------------------------------------------------
+    const bool staged = (tcol0 + TILE - 1 + REACH) <= W - 1;   // warp-uniform
+    if (staged) {
+        constexpr int ELEMS = HALO_ROWS * HALO_COLS;
+        for (int e = lane; e < ELEMS; e += 32) {
+            const int hr = e / HALO_COLS, hc = e - hr * HALO_COLS;
+            const int r = max(0, min(H - 1, trow0 - 1 + hr));
+            const int c = max(0, min(W - 1, tcol0 - 1 + hc));
+            const float* src = pixels + (img + (size_t)r * W + c) * C;
+            if (C == 4) cp_async_16(tile + e * 4, src);
+            else {
+#pragma unroll
+                for (int ch = 0; ch < C; ++ch) cp_async_4(tile + e * C + ch, src + ch);
+            }
+        }
+    }
+
+    // ---- own fragments (overlaps the staging copies) ---------------------------------------------------
+    Fragment own[2];
+#pragma unroll
+    for (int pix = 0; pix < 2; ++pix) own[pix] = fragment_at(itp_b, max(f_own[pix], -1), col, row0 + pix);
+    if (staged) cp_async_wait_all();
+    __syncwarp();
+
+    // ---- per-pixel terms -------------------------------------------------------------------------------------
+    PixelTerms term[2];
+    float sc[2][NS];    // scalars: [0,C) grad_pixels, C..C+2 = a,b,c
 #pragma unroll
     for (int pix = 0; pix < 2; ++pix) {
         const int row = row0 + pix;
         PixelTerms& T = term[pix];
         T.key_col = T.key_pos = -1;
-        T.bc0 = T.bc1 = T.bc2 = T.bp0 = T.bp1 = T.bp2 = T.a = T.b = T.c = 0.f;
+        T.bc0 = T.bc1 = T.bc2 = T.bp0 = T.bp1 = T.bp2 = 0.f;
 #pragma unroll
-        for (int ch = 0; ch < C; ++ch) gp[pix][ch] = 0.f;
-        if (col >= d.W || row >= d.H) continue;
-        const size_t p = ((size_t)b * d.H + row) * d.W + col;
-        load_pixel<C>(grad_pixels, p, gp[pix]);
-        const int f_own = __ldg(&ids[row * d.W + col]);
-        // grad_background: grad_pixels where uncovered, 0 elsewhere (:143-148, memset :247)
-        if (C == 4) {
-            const float4 o = f_own < 0 ? make_float4(gp[pix][0], gp[pix][1 % C], gp[pix][2 % C], gp[pix][3 % C])
-                                       : make_float4(0.f, 0.f, 0.f, 0.f);
-            reinterpret_cast<float4*>(grad_background)[p] = o;
-        } else {
-#pragma unroll
-            for (int ch = 0; ch < C; ++ch) grad_background[p * C + ch] = f_own < 0 ? gp[pix][ch] : 0.f;
-        }
-        // could anything reach this pixel?  (own coverage or a covered 4-neighbour)
-        bool near = f_own >= 0;
-        if (!near && col > 0 && row > 0 && col < d.W - 1 && row < d.H - 1) {
-            near = __ldg(&ids[row * d.W + col - 1]) >= 0 || __ldg(&ids[row * d.W + col + 1]) >= 0 ||
-                   __ldg(&ids[(row - 1) * d.W + col]) >= 0 || __ldg(&ids[(row + 1) * d.W + col]) >= 0;
-        }
-        if (!near) continue;
-        any_face = true;
-
-        const Fragment own = fragment_at(itp_b, f_own, col, row);
-        T.key_col = f_own;
-        if (f_own >= 0) { T.bc0 = own.g.x; T.bc1 = own.g.y; T.bc2 = own.g.z; }
+        for (int i = 0; i < NS; ++i) sc[pix][i] = (i < C) ? gp[pix][i % C] : 0.f;
+        if (f_own[pix] == -2) continue;
+        const Fragment& me = own[pix];
+        T.key_col = me.face;
+        if (me.face >= 0) { T.bc0 = me.g.x; T.bc1 = me.g.y; T.bc2 = me.g.z; }
 
         float sx[3], sy[3];
-        scharr_group<C, N0>(pixels, b, row, col, d, 0, sx, sy);
+        if (staged) scharr_smem<C, N0>(tile, lrow0 + pix + 1, lcol + 1, sx, sy);
+        else scharr_global<C, N0>(pixels, b, row, col, d, 0, sx, sy);
         int src0;
-        const Fragment pos0 = dilate(own, sx, sy, ids, itp_b, col, row, d, src0);
+        const Fragment pos0 = dilate(me, sx, sy, ids, itp_b, col, row, H, W, src0);
         float dLdx = 0.f, dLdy = 0.f;
 #pragma unroll
         for (int ch = 0; ch < N0; ++ch) { dLdx += gp[pix][ch] * sx[ch]; dLdy += gp[pix][ch] * sy[ch]; }
@@ -417,7 +477,7 @@ __global__ void __launch_bounds__(BWD_WARPS_PER_BLOCK * 32) backward_tile_kernel
             const float2 p2 = __ldg(reinterpret_cast<const float2*>(verts + (size_t)fr.v2 * 4));
             const float clip_x = fr.g.x * p0.x + fr.g.y * p1.x + fr.g.z * p2.x;
             const float clip_y = fr.g.x * p0.y + fr.g.y * p1.y + fr.g.z * p2.y;
-            const float inv_w = 1.f / fr.g.w;
+            const float inv_w = __frcp_rn(fr.g.w);
             a = gx * halfW * inv_w;
             bb = gy * halfH * inv_w;
             cc = -(a * clip_x + bb * clip_y) * inv_w;
@@ -426,18 +486,19 @@ __global__ void __launch_bounds__(BWD_WARPS_PER_BLOCK * 32) backward_tile_kernel
         if (pos0.face >= 0) {
             T.key_pos = pos0.face;
             T.bp0 = pos0.g.x; T.bp1 = pos0.g.y; T.bp2 = pos0.g.z;
-            position_terms(pos0, dLdx, dLdy, T.a, T.b, T.c);
+            position_terms(pos0, dLdx, dLdy, sc[pix][C], sc[pix][C + 1], sc[pix][C + 2]);
         }
         if (TWO_GROUPS) {
             float sx1[3], sy1[3];
-            scharr_group<C, 1>(pixels, b, row, col, d, 3, sx1, sy1);
+            if (staged) scharr_smem_c4_group1(tile, lrow0 + pix + 1, lcol + 1, sx1, sy1);
+            else scharr_global<C, 1>(pixels, b, row, col, d, 3, sx1, sy1);
             int src1;
-            const Fragment pos1 = dilate(own, sx1, sy1, ids, itp_b, col, row, d, src1);
+            const Fragment pos1 = dilate(me, sx1, sy1, ids, itp_b, col, row, H, W, src1);
             if (pos1.face >= 0) {
                 float a1, b1, c1;
                 position_terms(pos1, gp[pix][3 % C] * sx1[0], gp[pix][3 % C] * sy1[0], a1, b1, c1);
                 if (pos1.face == T.key_pos && src1 == src0) {
-                    T.a += a1; T.b += b1; T.c += c1;   // same fragment: same barycentrics
+                    sc[pix][C] += a1; sc[pix][C + 1] += b1; sc[pix][C + 2] += c1;   // same fragment: same barycentrics
                 } else {
                     // the two groups dilated differently (rare): this group's terms go out one by one
                     const int vid[3] = {pos1.v0, pos1.v1, pos1.v2};
@@ -452,9 +513,9 @@ __global__ void __launch_bounds__(BWD_WARPS_PER_BLOCK * 32) backward_tile_kernel
             }
         }
     }
-    if (!__any_sync(0xffffffffu, any_face)) return;
+    __syncwarp();   // all lanes are done with the staged tile before the next image overwrites it
 
-    // ---- per-face reduction ---------------------------------------------------------------------
+    // ---- per-face reduction -----------------------------------------------------------------------------------
     const int owner = transposed_reduce_owner<NV>(lane);
     int last = -1;
     while (true) {
@@ -472,8 +533,6 @@ __global__ void __launch_bounds__(BWD_WARPS_PER_BLOCK * 32) backward_tile_kernel
 
         float v[NV];
 #pragma unroll
-        for (int i = 0; i < NV; ++i) v[i] = 0.f;
-#pragma unroll
         for (int pix = 0; pix < 2; ++pix) {
             const PixelTerms& T = term[pix];
             const bool mc = T.key_col == f, mp = T.key_pos == f;
@@ -482,21 +541,21 @@ __global__ void __launch_bounds__(BWD_WARPS_PER_BLOCK * 32) backward_tile_kernel
 #pragma unroll
             for (int k = 0; k < 3; ++k) {
 #pragma unroll
-                for (int ch = 0; ch < C; ++ch) v[k * NS + ch] = fmaf(wc[k], gp[pix][ch], v[k * NS + ch]);
-                v[k * NS + C + 0] = fmaf(wp[k], T.a, v[k * NS + C + 0]);
-                v[k * NS + C + 1] = fmaf(wp[k], T.b, v[k * NS + C + 1]);
-                v[k * NS + C + 2] = fmaf(wp[k], T.c, v[k * NS + C + 2]);
+                for (int j = 0; j < NS; ++j) {
+                    const float w = (j < C) ? wc[k] : wp[k];
+                    v[k * NS + j] = (pix == 0) ? w * sc[pix][j] : fmaf(w, sc[pix][j], v[k * NS + j]);
+                }
             }
         }
         const float total = TransposedReduce<NV>::run(v, lane, 16);
         if (owner >= 0) {
             const int k = owner / NS, j = owner - k * NS;
-            // vertex ids of face f: uniform 16-byte load {sC, v0, v1, v2}
-            const int4 q = __ldg(reinterpret_cast<const int4*>(itp_b + f) + 2);
+            const int4 q = __ldg(reinterpret_cast<const int4*>(itp_b + f) + 2);   // {sC, v0, v1, v2}
             const int vid = (k == 0) ? q.y : (k == 1) ? q.z : q.w;
             float* dst = (j < C) ? (gcols + (size_t)vid * C + j) : (gverts + (size_t)vid * 4 + (j - C == 2 ? 3 : j - C));
             atomicAdd(dst, total);
         }
+    }
     }
 }
 
@@ -510,25 +569,27 @@ cudaError_t launch_backward(const float* vertices, const float* pixels, const fl
     if ((e = cudaMemsetAsync(grad_vertex_colors, 0, sizeof(float) * (size_t)d.B * d.V * d.C, stream)) != cudaSuccess) return e;
     const long long total_tiles = (long long)d.B * d.btiles;
     if (total_tiles == 0) return cudaSuccess;
-    const unsigned grid = (unsigned)((total_tiles + BWD_WARPS_PER_BLOCK - 1) / BWD_WARPS_PER_BLOCK);
     ScopedKernelTimer timer(2, stream);
     // fast path: the reference's default grouping of C in {1,3,4}; pointers vector-aligned where the kernel needs it
     const bool default_groups = (d.C == 1 && groups.n == 1) || (d.C == 3 && groups.n == 1 && groups.width[0] == 3) ||
                                 (d.C == 4 && groups.n == 2 && groups.width[0] == 3 && groups.width[1] == 1);
     const bool aligned4 = d.C != 4 || (((uintptr_t)pixels | (uintptr_t)grad_pixels | (uintptr_t)grad_background) % 16 == 0);
     const dim3 block(BWD_WARPS_PER_BLOCK * 32);
+    const dim3 grid2((unsigned)((d.btiles + BWD_WARPS_PER_BLOCK - 1) / BWD_WARPS_PER_BLOCK), (unsigned)min(d.B, 65535));
     if (default_groups && aligned4 && d.C == 4)
-        backward_tile_kernel<4><<<grid, block, 0, stream>>>(vertices, pixels, grad_pixels, face_ids, grad_background,
-                                                            grad_vertices, grad_vertex_colors, ws, d);
+        backward_tile_kernel<4><<<grid2, block, 0, stream>>>(vertices, pixels, grad_pixels, face_ids, grad_background,
+                                                             grad_vertices, grad_vertex_colors, ws, d);
     else if (default_groups && d.C == 3)
-        backward_tile_kernel<3><<<grid, block, 0, stream>>>(vertices, pixels, grad_pixels, face_ids, grad_background,
-                                                            grad_vertices, grad_vertex_colors, ws, d);
+        backward_tile_kernel<3><<<grid2, block, 0, stream>>>(vertices, pixels, grad_pixels, face_ids, grad_background,
+                                                             grad_vertices, grad_vertex_colors, ws, d);
     else if (default_groups && d.C == 1)
-        backward_tile_kernel<1><<<grid, block, 0, stream>>>(vertices, pixels, grad_pixels, face_ids, grad_background,
-                                                            grad_vertices, grad_vertex_colors, ws, d);
-    else
+        backward_tile_kernel<1><<<grid2, block, 0, stream>>>(vertices, pixels, grad_pixels, face_ids, grad_background,
+                                                             grad_vertices, grad_vertex_colors, ws, d);
+    else {
+        const unsigned grid = (unsigned)((total_tiles + BWD_WARPS_PER_BLOCK - 1) / BWD_WARPS_PER_BLOCK);
         backward_generic_kernel<<<grid, block, 0, stream>>>(vertices, pixels, grad_pixels, face_ids, grad_background,
                                                             grad_vertices, grad_vertex_colors, ws, d, groups);
+    }
     ++*launches;
     return cudaGetLastError();
 }
