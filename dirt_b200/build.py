@@ -33,7 +33,8 @@ def build(force=False, verbose=False):
     if not force and not is_stale():
         return SO_PATH
     srcs = [os.path.join(_HERE, 'csrc', s) for s in SOURCES]
-    cmd = [_nvcc()] + NVCC_FLAGS + (['-Xptxas', '-v'] if verbose else []) + ['-o', SO_PATH] + srcs
+    extra = os.environ.get('DIRT_NVCC_EXTRA', '').split()   # e.g. -DDIRT_RASTER_MIN_BLOCKS=5 (tuning experiments)
+    cmd = [_nvcc()] + NVCC_FLAGS + extra + (['-Xptxas', '-v'] if verbose else []) + ['-o', SO_PATH] + srcs
     proc = subprocess.run(cmd, capture_output=True, text=True)
     if proc.returncode != 0:
         raise RuntimeError('nvcc failed:\n' + ' '.join(cmd) + '\n' + proc.stdout + proc.stderr)

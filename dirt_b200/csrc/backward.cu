@@ -11,6 +11,9 @@
 namespace dirt {
 
 constexpr int BWD_WARPS_PER_BLOCK = 4;
+#ifndef DIRT_BWD_MIN_BLOCKS
+#define DIRT_BWD_MIN_BLOCKS 8   // <= 64 registers: measured best (profiles/r01_sweep_bounds.txt)
+#endif
 constexpr int TILE = 8;   // backward tile edge: one warp per 8x8 tile, two pixels per lane
 
 struct V3 { float x, y, z; };
@@ -216,24 +219,33 @@ __device__ __forceinline__ Fragment fragment_at(const TriInterp* __restrict__ it
     return fr;
 }
 
-// dilation (csrc/rasterise_grad_egl.cu:155-194): returns the fragment the position gradient goes to
-__device__ __forceinline__ Fragment dilate(const Fragment& own, const float (&sx)[3], const float (&sy)[3],
-                                           const int32_t* __restrict__ ids, const TriInterp* __restrict__ itp_b,
-                                           int col, int row, int H, int W, int& src)
+constexpr int IDS_COLS = TILE + 2;   // staged face-id halo: 10 x 10
+
+// dilation (csrc/rasterise_grad_egl.cu:155-194).  The preferred neighbour offset (buffer, y-up orientation) depends on
+// the group's Scharr sums; given the offset, the outcome depends on the visibility buffer only.
+__device__ __forceinline__ int dilation_dx(const float (&sx)[3], const float (&sy)[3], int col, int row)
+{
+    // returns dx in {-1,0,+1} with dy = +-(1 - |dx|): encode (dx,dy) as one int: dx + 3*dy
+    int dx = (l1(sx) > l1(sy)) ? 1 : 0, dy = 1 - dx;
+    if ((col + row) & 1) { dx = -dx; dy = -dy; }
+    return dx + 3 * dy;
+}
+
+// sid points at this pixel's entry of the staged id halo (row stride IDS_COLS)
+__device__ __forceinline__ Fragment dilate(const Fragment& own, int code, const int* __restrict__ sid,
+                                           const TriInterp* __restrict__ itp_b, int col, int row, int& src)
 {
     src = 0;
-    if (!(col > 0 && row > 0 && col < W - 1 && row < H - 1)) return own;
-    int dx = (l1(sx) > l1(sy)) ? 1 : 0, dy = 1 - dx;  // buffer (y-up) orientation
-    if ((col + row) & 1) { dx = -dx; dy = -dy; }
+    int dy = (code + 4) / 3 - 1;            // code = dx + 3*dy, dx,dy in {-1,0,1}
+    int dx = code - 3 * dy;
 #pragma unroll
     for (int attempt = 0; attempt < 2; ++attempt) {
-        const int nc = col + dx, nr = row - dy;
-        const int fn = __ldg(&ids[nr * W + nc]);
+        const int fn = sid[dx - dy * IDS_COLS];   // neighbour (col + dx, row - dy)
         if (fn >= 0 && fn != own.face) {
-            const Fragment n = fragment_at(itp_b, fn, nc, nr);
+            const Fragment n = fragment_at(itp_b, fn, col + dx, row - dy);
             const bool differs = (own.face < 0) || n.v0 != own.v0 || n.v1 != own.v1 || n.v2 != own.v2;
             if (differs && own.g.w > n.g.w) {
-                src = 1 + (dx + 1) + 3 * (dy + 1);   // distinguishes the four neighbours
+                src = 5 + dx + 3 * dy;   // distinguishes the four neighbours, never 0
                 return n;
             }
         }
@@ -270,16 +282,31 @@ __device__ __forceinline__ void scharr_smem(const float* __restrict__ tile, int 
     }
 }
 
-// the 1-wide second group of C == 4 (channel 3): comp k = channel 3 of the pixel k places to the right
-__device__ __forceinline__ void scharr_smem_c4_group1(const float* __restrict__ tile, int lr, int lc, float (&sx)[3], float (&sy)[3])
+// C == 4, groups {3,1}: both groups from 15 vector taps (rows lr-1..lr+1, columns lc-1..lc+3).
+// Group {0,1,2} uses .xyz of columns lc-1..lc+1; group {3} uses .w, comp k being the pixel k places to the right.
+__device__ __forceinline__ void scharr_smem_c4(const float* __restrict__ tile, int lr, int lc, float (&sx)[3], float (&sy)[3],
+                                               float (&sx1)[3], float (&sy1)[3])
 {
-    auto T = [&](int dr, int dc, int k) -> float { return tile[((lr + dr) * HALO_COLS + lc + dc + k) * 4 + 3]; };
+    const float4* t4 = reinterpret_cast<const float4*>(tile) + (lr * HALO_COLS + lc);
+    float4 up[5], mid[5], dn[5];   // image rows lr-1 (at oy=+1), lr, lr+1 (at oy=-1); columns lc-1 .. lc+3
+#pragma unroll
+    for (int j = 0; j < 5; ++j) {
+        up[j] = t4[-HALO_COLS + j - 1];
+        mid[j] = t4[j - 1];
+        dn[j] = t4[HALO_COLS + j - 1];
+    }
+    // at(ox,oy) is image (row - oy, col + ox):  a_mm = dn[0], a_mp = up[0], a_pm = dn[2], a_pp = up[2], a_m0 = mid[0],
+    // a_p0 = mid[2], a_0m = dn[1], a_0p = up[1]
+    sx[0] = scharr_comp(dn[0].x, up[0].x, dn[2].x, up[2].x, mid[0].x, mid[2].x);
+    sx[1] = scharr_comp(dn[0].y, up[0].y, dn[2].y, up[2].y, mid[0].y, mid[2].y);
+    sx[2] = scharr_comp(dn[0].z, up[0].z, dn[2].z, up[2].z, mid[0].z, mid[2].z);
+    sy[0] = scharr_comp(dn[0].x, dn[2].x, up[0].x, up[2].x, dn[1].x, up[1].x);
+    sy[1] = scharr_comp(dn[0].y, dn[2].y, up[0].y, up[2].y, dn[1].y, up[1].y);
+    sy[2] = scharr_comp(dn[0].z, dn[2].z, up[0].z, up[2].z, dn[1].z, up[1].z);
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
-        const float a_mm = T(+1, -1, k), a_mp = T(-1, -1, k), a_pm = T(+1, +1, k), a_pp = T(-1, +1, k);
-        const float a_m0 = T(0, -1, k), a_p0 = T(0, +1, k), a_0m = T(+1, 0, k), a_0p = T(-1, 0, k);
-        sx[k] = scharr_comp(a_mm, a_mp, a_pm, a_pp, a_m0, a_p0);
-        sy[k] = scharr_comp(a_mm, a_pm, a_mp, a_pp, a_0m, a_0p);
+        sx1[k] = scharr_comp(dn[k].w, up[k].w, dn[k + 2].w, up[k + 2].w, mid[k].w, mid[k + 2].w);
+        sy1[k] = scharr_comp(dn[k].w, dn[k + 2].w, up[k].w, up[k + 2].w, dn[k + 1].w, up[k + 1].w);
     }
 }
 
@@ -350,7 +377,7 @@ __device__ __forceinline__ int transposed_reduce_owner(int lane)
 }
 
 template <int C>
-__global__ void __launch_bounds__(BWD_WARPS_PER_BLOCK * 32) backward_tile_kernel(
+__global__ void __launch_bounds__(BWD_WARPS_PER_BLOCK * 32, DIRT_BWD_MIN_BLOCKS) backward_tile_kernel(
     const float* __restrict__ vertices, const float* __restrict__ pixels, const float* __restrict__ grad_pixels,
     const int32_t* __restrict__ face_ids, float* __restrict__ grad_background, float* __restrict__ grad_vertices,
     float* __restrict__ grad_vertex_colors, Workspace ws, Dims d)
@@ -362,18 +389,21 @@ __global__ void __launch_bounds__(BWD_WARPS_PER_BLOCK * 32) backward_tile_kernel
     constexpr int REACH = (C == 3) ? 1 : 3;    // columns to the right of the pixel that its taps read
 
     __shared__ __align__(16) float tile_all[BWD_WARPS_PER_BLOCK][HALO_ROWS * HALO_COLS * C];
+    __shared__ int ids_all[BWD_WARPS_PER_BLOCK][IDS_COLS * IDS_COLS];
 
+    // grid: x = groups of BWD_WARPS_PER_BLOCK tiles along a tile row, y = tile row, z = image
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int t = blockIdx.x * BWD_WARPS_PER_BLOCK + warp;
-    if (t >= d.btiles) return;
-    const int ty = t / d.btiles_x, tx = t - ty * d.btiles_x;
+    const int tx = blockIdx.x * BWD_WARPS_PER_BLOCK + warp, ty = blockIdx.y;
+    if (tx >= d.btiles_x) return;
     const int tcol0 = tx * TILE, trow0 = ty * TILE;
     const int lcol = lane & 7, lrow0 = (lane >> 3) * 2;
     const int col = tcol0 + lcol, row0 = trow0 + lrow0;
     const int H = d.H, W = d.W;
     float* tile = tile_all[warp];
+    int* sids = ids_all[warp];
+    const int* sid0 = sids + (lrow0 + 1) * IDS_COLS + lcol + 1;   // this lane's first pixel inside the id halo
 
-    for (int b = blockIdx.y; b < d.B; b += gridDim.y) {
+    for (int b = blockIdx.z; b < d.B; b += gridDim.z) {
     const TriInterp* itp_b = ws.itp + (size_t)b * d.F;
     const float* verts = vertices + (size_t)b * d.V * 4;
     const int32_t* ids = face_ids + (size_t)b * H * W;
@@ -382,19 +412,22 @@ __global__ void __launch_bounds__(BWD_WARPS_PER_BLOCK * 32) backward_tile_kernel
     const size_t img = (size_t)b * H * W;
     const float halfW = 0.5f * (float)W, halfH = 0.5f * (float)H;
 
-    // ---- own faces, grad_pixels, grad_background; does anything reach this tile? --------------------
-    int f_own[2];
+    // ---- stage the face-id halo (10x10, -1 outside the frame); fetch grad_pixels meanwhile -----------------
+    __syncwarp();   // the previous image's readers are done
+    for (int e = lane; e < IDS_COLS * IDS_COLS; e += 32) {
+        const int hr = e / IDS_COLS, hc = e - hr * IDS_COLS;
+        const int r = trow0 - 1 + hr, c = tcol0 - 1 + hc;
+        if (r >= 0 && r < H && c >= 0 && c < W) cp_async_4(sids + e, ids + r * W + c);
+        else sids[e] = -1;
+    }
     float gp[2][C];
-    bool near = false;
 #pragma unroll
     for (int pix = 0; pix < 2; ++pix) {
         const int row = row0 + pix;
-        f_own[pix] = -1;
 #pragma unroll
         for (int ch = 0; ch < C; ++ch) gp[pix][ch] = 0.f;
         if (col >= W || row >= H) continue;
-        const int pi = row * W + col;
-        const size_t p = img + pi;
+        const size_t p = img + (size_t)row * W + col;
         if (C == 4) {
             const float4 v = __ldg(reinterpret_cast<const float4*>(grad_pixels) + p);
             gp[pix][0] = v.x; gp[pix][1 % C] = v.y; gp[pix][2 % C] = v.z; gp[pix][3 % C] = v.w;
@@ -402,8 +435,21 @@ __global__ void __launch_bounds__(BWD_WARPS_PER_BLOCK * 32) backward_tile_kernel
 #pragma unroll
             for (int ch = 0; ch < C; ++ch) gp[pix][ch] = __ldg(grad_pixels + p * C + ch);
         }
-        const int f = __ldg(&ids[pi]);
-        f_own[pix] = f;
+    }
+    cp_async_wait_all();
+    __syncwarp();
+
+    // ---- grad_background; does anything reach this tile? -------------------------------------------------------
+    int f_own[2];
+    bool near = false;
+#pragma unroll
+    for (int pix = 0; pix < 2; ++pix) {
+        const int row = row0 + pix;
+        f_own[pix] = -2;
+        if (col >= W || row >= H) continue;
+        const size_t p = img + (size_t)row * W + col;
+        const int* sid = sid0 + pix * IDS_COLS;
+        const int f = sid[0];
         // grad_background: grad_pixels where uncovered, 0 elsewhere (:143-148, memset :247)
         if (C == 4) {
             reinterpret_cast<float4*>(grad_background)[p] =
@@ -412,11 +458,11 @@ __global__ void __launch_bounds__(BWD_WARPS_PER_BLOCK * 32) backward_tile_kernel
 #pragma unroll
             for (int ch = 0; ch < C; ++ch) grad_background[p * C + ch] = f < 0 ? gp[pix][ch] : 0.f;
         }
-        // own coverage, or a covered 4-neighbour that could dilate into this pixel
+        // own coverage, or (interior pixels only) a covered 4-neighbour that could dilate into this pixel
         bool n = f >= 0;
         if (!n && col > 0 && row > 0 && col < W - 1 && row < H - 1)
-            n = __ldg(&ids[pi - 1]) >= 0 || __ldg(&ids[pi + 1]) >= 0 || __ldg(&ids[pi - W]) >= 0 || __ldg(&ids[pi + W]) >= 0;
-        if (!n) f_own[pix] = -2;   // nothing can reach this pixel
+            n = (sid[-1] & sid[1] & sid[-IDS_COLS] & sid[IDS_COLS]) >= 0;   // any of the four non-negative
+        if (n) f_own[pix] = f;   // -2: nothing can reach this pixel
         near = near || n;
     }
     if (!__any_sync(0xffffffffu, near)) continue;
@@ -440,8 +486,14 @@ __global__ void __launch_bounds__(BWD_WARPS_PER_BLOCK * 32) backward_tile_kernel
 
     // ---- own fragments (overlaps the staging copies) ---------------------------------------------------
     Fragment own[2];
-#pragma unroll
-    for (int pix = 0; pix < 2; ++pix) own[pix] = fragment_at(itp_b, max(f_own[pix], -1), col, row0 + pix);
+    own[0] = fragment_at(itp_b, max(f_own[0], -1), col, row0);
+    if (f_own[1] == f_own[0] && f_own[0] >= 0) {
+        // same face one row down: only the G-buffer entry changes
+        own[1] = own[0];
+        own[1].g = exact::gbuffer_at(load_interp(itp_b + f_own[1]), col, row0 + 1);
+    } else {
+        own[1] = fragment_at(itp_b, max(f_own[1], -1), col, row0 + 1);
+    }
     if (staged) cp_async_wait_all();
     __syncwarp();
 
@@ -458,14 +510,25 @@ __global__ void __launch_bounds__(BWD_WARPS_PER_BLOCK * 32) backward_tile_kernel
         for (int i = 0; i < NS; ++i) sc[pix][i] = (i < C) ? gp[pix][i % C] : 0.f;
         if (f_own[pix] == -2) continue;
         const Fragment& me = own[pix];
+        const int* sid = sid0 + pix * IDS_COLS;
+        const bool interior = col > 0 && row > 0 && col < W - 1 && row < H - 1;
         T.key_col = me.face;
         if (me.face >= 0) { T.bc0 = me.g.x; T.bc1 = me.g.y; T.bc2 = me.g.z; }
 
-        float sx[3], sy[3];
-        if (staged) scharr_smem<C, N0>(tile, lrow0 + pix + 1, lcol + 1, sx, sy);
-        else scharr_global<C, N0>(pixels, b, row, col, d, 0, sx, sy);
-        int src0;
-        const Fragment pos0 = dilate(me, sx, sy, ids, itp_b, col, row, H, W, src0);
+        float sx[3], sy[3], sx1[3], sy1[3];
+        if (staged) {
+            if (C == 4) scharr_smem_c4(tile, lrow0 + pix + 1, lcol + 1, sx, sy, sx1, sy1);
+            else scharr_smem<C, N0>(tile, lrow0 + pix + 1, lcol + 1, sx, sy);
+        } else {
+            scharr_global<C, N0>(pixels, b, row, col, d, 0, sx, sy);
+            if (TWO_GROUPS) scharr_global<C, 1>(pixels, b, row, col, d, 3, sx1, sy1);
+        }
+        int src0 = 0, code0 = 0;
+        Fragment pos0 = me;
+        if (interior) {
+            code0 = dilation_dx(sx, sy, col, row);
+            pos0 = dilate(me, code0, sid, itp_b, col, row, src0);
+        }
         float dLdx = 0.f, dLdy = 0.f;
 #pragma unroll
         for (int ch = 0; ch < N0; ++ch) { dLdx += gp[pix][ch] * sx[ch]; dLdy += gp[pix][ch] * sy[ch]; }
@@ -483,37 +546,41 @@ __global__ void __launch_bounds__(BWD_WARPS_PER_BLOCK * 32) backward_tile_kernel
             cc = -(a * clip_x + bb * clip_y) * inv_w;
         };
 
+        if (TWO_GROUPS) {
+            // the second group dilates to the same fragment whenever it prefers the same neighbour (the usual case):
+            // the outcome of a dilation depends on the offset and on the visibility buffer only
+            const float gx1 = gp[pix][3 % C] * sx1[0], gy1 = gp[pix][3 % C] * sy1[0];
+            const int code1 = interior ? dilation_dx(sx1, sy1, col, row) : 0;
+            if (code1 == code0) {
+                dLdx += gx1; dLdy += gy1;
+            } else {
+                int src1;
+                const Fragment pos1 = dilate(me, code1, sid, itp_b, col, row, src1);
+                if (pos1.face >= 0) {
+                    if (pos1.face == pos0.face && src1 == src0) {
+                        dLdx += gx1; dLdy += gy1;
+                    } else {
+                        // the two groups dilated differently (rare): this group's terms go out one by one
+                        float a1, b1, c1;
+                        position_terms(pos1, gx1, gy1, a1, b1, c1);
+                        const int vid[3] = {pos1.v0, pos1.v1, pos1.v2};
+                        const float bary[3] = {pos1.g.x, pos1.g.y, pos1.g.z};
+#pragma unroll
+                        for (int k = 0; k < 3; ++k) {
+                            atomicAdd(&gverts[(size_t)vid[k] * 4 + 0], a1 * bary[k]);
+                            atomicAdd(&gverts[(size_t)vid[k] * 4 + 1], b1 * bary[k]);
+                            atomicAdd(&gverts[(size_t)vid[k] * 4 + 3], c1 * bary[k]);
+                        }
+                    }
+                }
+            }
+        }
         if (pos0.face >= 0) {
             T.key_pos = pos0.face;
             T.bp0 = pos0.g.x; T.bp1 = pos0.g.y; T.bp2 = pos0.g.z;
             position_terms(pos0, dLdx, dLdy, sc[pix][C], sc[pix][C + 1], sc[pix][C + 2]);
         }
-        if (TWO_GROUPS) {
-            float sx1[3], sy1[3];
-            if (staged) scharr_smem_c4_group1(tile, lrow0 + pix + 1, lcol + 1, sx1, sy1);
-            else scharr_global<C, 1>(pixels, b, row, col, d, 3, sx1, sy1);
-            int src1;
-            const Fragment pos1 = dilate(me, sx1, sy1, ids, itp_b, col, row, H, W, src1);
-            if (pos1.face >= 0) {
-                float a1, b1, c1;
-                position_terms(pos1, gp[pix][3 % C] * sx1[0], gp[pix][3 % C] * sy1[0], a1, b1, c1);
-                if (pos1.face == T.key_pos && src1 == src0) {
-                    sc[pix][C] += a1; sc[pix][C + 1] += b1; sc[pix][C + 2] += c1;   // same fragment: same barycentrics
-                } else {
-                    // the two groups dilated differently (rare): this group's terms go out one by one
-                    const int vid[3] = {pos1.v0, pos1.v1, pos1.v2};
-                    const float bary[3] = {pos1.g.x, pos1.g.y, pos1.g.z};
-#pragma unroll
-                    for (int k = 0; k < 3; ++k) {
-                        atomicAdd(&gverts[(size_t)vid[k] * 4 + 0], a1 * bary[k]);
-                        atomicAdd(&gverts[(size_t)vid[k] * 4 + 1], b1 * bary[k]);
-                        atomicAdd(&gverts[(size_t)vid[k] * 4 + 3], c1 * bary[k]);
-                    }
-                }
-            }
-        }
     }
-    __syncwarp();   // all lanes are done with the staged tile before the next image overwrites it
 
     // ---- per-face reduction -----------------------------------------------------------------------------------
     const int owner = transposed_reduce_owner<NV>(lane);
@@ -575,7 +642,8 @@ cudaError_t launch_backward(const float* vertices, const float* pixels, const fl
                                 (d.C == 4 && groups.n == 2 && groups.width[0] == 3 && groups.width[1] == 1);
     const bool aligned4 = d.C != 4 || (((uintptr_t)pixels | (uintptr_t)grad_pixels | (uintptr_t)grad_background) % 16 == 0);
     const dim3 block(BWD_WARPS_PER_BLOCK * 32);
-    const dim3 grid2((unsigned)((d.btiles + BWD_WARPS_PER_BLOCK - 1) / BWD_WARPS_PER_BLOCK), (unsigned)min(d.B, 65535));
+    const dim3 grid2((unsigned)((d.btiles_x + BWD_WARPS_PER_BLOCK - 1) / BWD_WARPS_PER_BLOCK), (unsigned)d.btiles_y,
+                     (unsigned)min(d.B, 65535));
     if (default_groups && aligned4 && d.C == 4)
         backward_tile_kernel<4><<<grid2, block, 0, stream>>>(vertices, pixels, grad_pixels, face_ids, grad_background,
                                                              grad_vertices, grad_vertex_colors, ws, d);

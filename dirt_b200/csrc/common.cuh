@@ -174,7 +174,7 @@ __device__ __forceinline__ float4 gbuffer_at(const TriInterp& t, int col, int ro
 {
     const float dc = (float)(col - t.cref), dr = (float)(row - t.rref);
     const float S = __fmaf_rn(t.sA, dc, __fmaf_rn(t.sB, dr, t.sC));
-    const float cw = __fdiv_rn(1.0f, S);
+    const float cw = __frcp_rn(S);   // correctly rounded reciprocal == the oracle's IEEE 1.0f / S
     const float q0 = __fmaf_rn(t.q0A, dc, __fmaf_rn(t.q0B, dr, t.q0C));
     const float q1 = __fmaf_rn(t.q1A, dc, __fmaf_rn(t.q1B, dr, t.q1C));
     const float b0 = __fmul_rn(q0, cw), b1 = __fmul_rn(q1, cw);

@@ -21,6 +21,9 @@
 namespace dirt {
 
 constexpr int WARPS_PER_BLOCK = 4;
+#ifndef DIRT_RASTER_MIN_BLOCKS
+#define DIRT_RASTER_MIN_BLOCKS 8   // <= 64 registers: measured best (profiles/r01_sweep_bounds.txt)
+#endif
 
 struct __align__(16) Slot {
     int32_t A0, B0, A1, B1;
@@ -223,18 +226,19 @@ __device__ __forceinline__ void shade_pixel(const TriInterp& ti, int col, int ro
 
 // MODE 0: colour forward (pixels [+ face ids]); MODE 1: visibility (face ids and/or G-buffer)
 template <int MODE, int CT>
-__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) raster_kernel(
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, DIRT_RASTER_MIN_BLOCKS) raster_kernel(
     const float* __restrict__ vertices, const float* __restrict__ background,
     const float* __restrict__ vertex_colors, float* __restrict__ pixels, int32_t* __restrict__ face_ids_out,
     float* __restrict__ gbuffer_out, Workspace ws, Dims d)
 {
     __shared__ Slot slots_all[WARPS_PER_BLOCK][32];
+    // grid: x = groups of WARPS_PER_BLOCK tiles along a tile row, y = tile row, z = image
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int t = blockIdx.x * WARPS_PER_BLOCK + warp;
-    if (t >= d.tiles) return;
-    for (int b = blockIdx.y; b < d.B; b += gridDim.y) {   // gridDim.y == B unless B exceeds the grid limit
-    const int ty = t / d.tiles_x, tx = t - ty * d.tiles_x;
+    const int tx = blockIdx.x * WARPS_PER_BLOCK + warp, ty = blockIdx.y;
+    if (tx >= d.tiles_x) return;
+    const int t = ty * d.tiles_x + tx;
     const int tcol0 = tx * TILE_W, trow0 = ty * TILE_H;
+    for (int b = blockIdx.z; b < d.B; b += gridDim.z) {   // gridDim.z == B unless B exceeds the grid limit
 
     const TriCov* cov_b = ws.cov + (size_t)b * d.F;
     const TriInterp* itp_b = ws.itp + (size_t)b * d.F;
@@ -292,7 +296,7 @@ cudaError_t launch_raster_forward(const float* vertices, const float* background
                                   int* launches)
 {
     if ((long long)d.B * d.tiles == 0) return cudaSuccess;
-    const dim3 grid((unsigned)((d.tiles + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK), (unsigned)min(d.B, 65535));
+    const dim3 grid((unsigned)((d.tiles_x + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK), (unsigned)d.tiles_y, (unsigned)min(d.B, 65535));
     ScopedKernelTimer timer(1, stream);
     const bool vec4 = d.C == 4 && ((uintptr_t)background % 16 == 0) && ((uintptr_t)pixels % 16 == 0) &&
                       ((uintptr_t)vertex_colors % 16 == 0);
@@ -310,7 +314,7 @@ cudaError_t launch_raster_visibility(const float* vertices, int32_t* face_ids, f
                                      cudaStream_t stream, int* launches)
 {
     if ((long long)d.B * d.tiles == 0) return cudaSuccess;
-    const dim3 grid((unsigned)((d.tiles + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK), (unsigned)min(d.B, 65535));
+    const dim3 grid((unsigned)((d.tiles_x + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK), (unsigned)d.tiles_y, (unsigned)min(d.B, 65535));
     raster_kernel<1, 0><<<grid, WARPS_PER_BLOCK * 32, 0, stream>>>(vertices, nullptr, nullptr, nullptr, face_ids, gbuffer, ws, d);
     ++*launches;
     return cudaGetLastError();
