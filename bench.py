@@ -157,7 +157,7 @@ class PreparedStep:
         rc = self.lib.dirt_rasterise_backward(self._p(self.vertices), self._p(self.faces), self._p(self.pixels),
                                               self._p(self.grad_pixels), self._p(self.face_ids), self._p(self.grad_background),
                                               self._p(self.grad_vertices), self._p(self.grad_vertex_colors), B, H, W, C, V, F,
-                                              None, 0, self._p(self.workspace), self.ws_bytes, stream)
+                                              None, 0, 1, self._p(self.workspace), self.ws_bytes, stream)
         self._check(rc, 'RasteriseGrad')
         return self.lib.dirt_last_launch_count()
 

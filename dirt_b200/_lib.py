@@ -41,7 +41,7 @@ def lib():
     L.dirt_rasterise_forward.restype = i
     L.dirt_rasterise_forward.argtypes = [vp] * 6 + [i] * 6 + [vp, sz, vp]
     L.dirt_rasterise_backward.restype = i
-    L.dirt_rasterise_backward.argtypes = [vp] * 8 + [i] * 6 + [ctypes.POINTER(ctypes.c_int), i, vp, sz, vp]
+    L.dirt_rasterise_backward.argtypes = [vp] * 8 + [i] * 6 + [ctypes.POINTER(ctypes.c_int), i, i, vp, sz, vp]
     L.dirt_rasterise_visibility.restype = i
     L.dirt_rasterise_visibility.argtypes = [vp] * 4 + [i] * 5 + [vp, sz, vp]
     L.dirt_kernel_timer_enable.restype = i

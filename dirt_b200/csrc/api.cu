@@ -24,7 +24,7 @@ extern "C" const char* dirt_error_string(int code)
     }
 }
 
-extern "C" int dirt_abi_version(void) { return 1; }
+extern "C" int dirt_abi_version(void) { return 2; }
 
 namespace dirt {
 KernelTimer& kernel_timer()
@@ -169,8 +169,8 @@ extern "C" int dirt_rasterise_visibility(const float* vertices, const int32_t* f
 extern "C" int dirt_rasterise_backward(const float* vertices, const int32_t* faces, const float* pixels,
                                        const float* grad_pixels, const int32_t* face_ids, float* grad_background,
                                        float* grad_vertices, float* grad_vertex_colors, int B, int H, int W, int C, int V,
-                                       int F, const int* channel_groups, int n_groups, void* workspace,
-                                       size_t workspace_bytes, void* cuda_stream)
+                                       int F, const int* channel_groups, int n_groups, int workspace_holds_setup,
+                                       void* workspace, size_t workspace_bytes, void* cuda_stream)
 {
     int launches = 0;
     t_last_launches = 0;
@@ -197,7 +197,7 @@ extern "C" int dirt_rasterise_backward(const float* vertices, const int32_t* fac
         CUDA_TRY(launch_setup_and_bin(vertices, faces, ws, d, stream, &launches));
         CUDA_TRY(launch_raster_visibility(vertices, ws.face_ids, nullptr, ws, d, stream, &launches));
         ids = ws.face_ids;
-    } else {
+    } else if (!workspace_holds_setup) {
         CUDA_TRY(launch_setup_only(vertices, faces, ws, d, stream, &launches));
     }
     CUDA_TRY(launch_backward(vertices, pixels, grad_pixels, ids, grad_background, grad_vertices, grad_vertex_colors, ws, d,

@@ -219,37 +219,36 @@ __device__ __forceinline__ Fragment fragment_at(const TriInterp* __restrict__ it
     return fr;
 }
 
-constexpr int IDS_COLS = TILE + 2;   // staged face-id halo: 10 x 10
-
 // dilation (csrc/rasterise_grad_egl.cu:155-194).  The preferred neighbour offset (buffer, y-up orientation) depends on
 // the group's Scharr sums; given the offset, the outcome depends on the visibility buffer only.
-__device__ __forceinline__ int dilation_dx(const float (&sx)[3], const float (&sy)[3], int col, int row)
+// Offsets are encoded as code = dx + 3*dy with (dx,dy) in {(1,0),(-1,0),(0,1),(0,-1)}: 1, -1, 3, -3.
+__device__ __forceinline__ int dilation_code(const float (&sx)[3], const float (&sy)[3], int col, int row)
 {
-    // returns dx in {-1,0,+1} with dy = +-(1 - |dx|): encode (dx,dy) as one int: dx + 3*dy
-    int dx = (l1(sx) > l1(sy)) ? 1 : 0, dy = 1 - dx;
-    if ((col + row) & 1) { dx = -dx; dy = -dy; }
-    return dx + 3 * dy;
+    int code = (l1(sx) > l1(sy)) ? 1 : 3;
+    if ((col + row) & 1) code = -code;
+    return code;
 }
 
-// sid points at this pixel's entry of the staged id halo (row stride IDS_COLS)
-__device__ __forceinline__ Fragment dilate(const Fragment& own, int code, const int* __restrict__ sid,
+struct Neighbours { int left, right, up, down; };   // face ids at (col-1,row), (col+1,row), (col,row-1), (col,row+1)
+
+__device__ __forceinline__ Fragment dilate(const Fragment& own, int code, const Neighbours& nb,
                                            const TriInterp* __restrict__ itp_b, int col, int row, int& src)
 {
     src = 0;
-    int dy = (code + 4) / 3 - 1;            // code = dx + 3*dy, dx,dy in {-1,0,1}
-    int dx = code - 3 * dy;
 #pragma unroll
     for (int attempt = 0; attempt < 2; ++attempt) {
-        const int fn = sid[dx - dy * IDS_COLS];   // neighbour (col + dx, row - dy)
+        // buffer offset (dx,dy) is image (col + dx, row - dy)
+        const int fn = (code == 1) ? nb.right : (code == -1) ? nb.left : (code == 3) ? nb.up : nb.down;
         if (fn >= 0 && fn != own.face) {
+            const int dx = (code == 1) - (code == -1), dy = (code == 3) - (code == -3);
             const Fragment n = fragment_at(itp_b, fn, col + dx, row - dy);
             const bool differs = (own.face < 0) || n.v0 != own.v0 || n.v1 != own.v1 || n.v2 != own.v2;
             if (differs && own.g.w > n.g.w) {
-                src = 5 + dx + 3 * dy;   // distinguishes the four neighbours, never 0
+                src = code;   // distinguishes the four neighbours, never 0
                 return n;
             }
         }
-        dx = -dx; dy = -dy;
+        code = -code;
     }
     return own;
 }
@@ -389,7 +388,6 @@ __global__ void __launch_bounds__(BWD_WARPS_PER_BLOCK * 32, DIRT_BWD_MIN_BLOCKS)
     constexpr int REACH = (C == 3) ? 1 : 3;    // columns to the right of the pixel that its taps read
 
     __shared__ __align__(16) float tile_all[BWD_WARPS_PER_BLOCK][HALO_ROWS * HALO_COLS * C];
-    __shared__ int ids_all[BWD_WARPS_PER_BLOCK][IDS_COLS * IDS_COLS];
 
     // grid: x = groups of BWD_WARPS_PER_BLOCK tiles along a tile row, y = tile row, z = image
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -400,8 +398,6 @@ __global__ void __launch_bounds__(BWD_WARPS_PER_BLOCK * 32, DIRT_BWD_MIN_BLOCKS)
     const int col = tcol0 + lcol, row0 = trow0 + lrow0;
     const int H = d.H, W = d.W;
     float* tile = tile_all[warp];
-    int* sids = ids_all[warp];
-    const int* sid0 = sids + (lrow0 + 1) * IDS_COLS + lcol + 1;   // this lane's first pixel inside the id halo
 
     for (int b = blockIdx.z; b < d.B; b += gridDim.z) {
     const TriInterp* itp_b = ws.itp + (size_t)b * d.F;
@@ -412,14 +408,17 @@ __global__ void __launch_bounds__(BWD_WARPS_PER_BLOCK * 32, DIRT_BWD_MIN_BLOCKS)
     const size_t img = (size_t)b * H * W;
     const float halfW = 0.5f * (float)W, halfH = 0.5f * (float)H;
 
-    // ---- stage the face-id halo (10x10, -1 outside the frame); fetch grad_pixels meanwhile -----------------
-    __syncwarp();   // the previous image's readers are done
-    for (int e = lane; e < IDS_COLS * IDS_COLS; e += 32) {
-        const int hr = e / IDS_COLS, hc = e - hr * IDS_COLS;
-        const int r = trow0 - 1 + hr, c = tcol0 - 1 + hc;
-        if (r >= 0 && r < H && c >= 0 && c < W) cp_async_4(sids + e, ids + r * W + c);
-        else sids[e] = -1;
-    }
+    // ---- this lane's two pixels and their six outer neighbours in the visibility buffer; grad_pixels ------------
+    // rows row0-1 .. row0+2 at column col, and columns col-1 / col+1 at rows row0, row0+1 (-1 outside the frame)
+    const bool col_in = col < W;
+    auto id_at = [&](int r, int c) -> int { return (r >= 0 && r < H && c >= 0 && c < W) ? __ldg(&ids[r * W + c]) : -1; };
+    const int id_up = col_in ? id_at(row0 - 1, col) : -1, id_0 = col_in ? id_at(row0, col) : -1;
+    const int id_1 = col_in ? id_at(row0 + 1, col) : -1, id_dn = col_in ? id_at(row0 + 2, col) : -1;
+    const int id_l0 = id_at(row0, col - 1), id_r0 = id_at(row0, col + 1);
+    const int id_l1 = id_at(row0 + 1, col - 1), id_r1 = id_at(row0 + 1, col + 1);
+    Neighbours nbs[2];
+    nbs[0].left = id_l0; nbs[0].right = id_r0; nbs[0].up = id_up; nbs[0].down = id_1;
+    nbs[1].left = id_l1; nbs[1].right = id_r1; nbs[1].up = id_0; nbs[1].down = id_dn;
     float gp[2][C];
 #pragma unroll
     for (int pix = 0; pix < 2; ++pix) {
@@ -436,8 +435,6 @@ __global__ void __launch_bounds__(BWD_WARPS_PER_BLOCK * 32, DIRT_BWD_MIN_BLOCKS)
             for (int ch = 0; ch < C; ++ch) gp[pix][ch] = __ldg(grad_pixels + p * C + ch);
         }
     }
-    cp_async_wait_all();
-    __syncwarp();
 
     // ---- grad_background; does anything reach this tile? -------------------------------------------------------
     int f_own[2];
@@ -448,8 +445,7 @@ __global__ void __launch_bounds__(BWD_WARPS_PER_BLOCK * 32, DIRT_BWD_MIN_BLOCKS)
         f_own[pix] = -2;
         if (col >= W || row >= H) continue;
         const size_t p = img + (size_t)row * W + col;
-        const int* sid = sid0 + pix * IDS_COLS;
-        const int f = sid[0];
+        const int f = pix ? id_1 : id_0;
         // grad_background: grad_pixels where uncovered, 0 elsewhere (:143-148, memset :247)
         if (C == 4) {
             reinterpret_cast<float4*>(grad_background)[p] =
@@ -461,7 +457,7 @@ __global__ void __launch_bounds__(BWD_WARPS_PER_BLOCK * 32, DIRT_BWD_MIN_BLOCKS)
         // own coverage, or (interior pixels only) a covered 4-neighbour that could dilate into this pixel
         bool n = f >= 0;
         if (!n && col > 0 && row > 0 && col < W - 1 && row < H - 1)
-            n = (sid[-1] & sid[1] & sid[-IDS_COLS] & sid[IDS_COLS]) >= 0;   // any of the four non-negative
+            n = (nbs[pix].left & nbs[pix].right & nbs[pix].up & nbs[pix].down) >= 0;   // any of the four non-negative
         if (n) f_own[pix] = f;   // -2: nothing can reach this pixel
         near = near || n;
     }
@@ -510,7 +506,6 @@ __global__ void __launch_bounds__(BWD_WARPS_PER_BLOCK * 32, DIRT_BWD_MIN_BLOCKS)
         for (int i = 0; i < NS; ++i) sc[pix][i] = (i < C) ? gp[pix][i % C] : 0.f;
         if (f_own[pix] == -2) continue;
         const Fragment& me = own[pix];
-        const int* sid = sid0 + pix * IDS_COLS;
         const bool interior = col > 0 && row > 0 && col < W - 1 && row < H - 1;
         T.key_col = me.face;
         if (me.face >= 0) { T.bc0 = me.g.x; T.bc1 = me.g.y; T.bc2 = me.g.z; }
@@ -526,8 +521,8 @@ __global__ void __launch_bounds__(BWD_WARPS_PER_BLOCK * 32, DIRT_BWD_MIN_BLOCKS)
         int src0 = 0, code0 = 0;
         Fragment pos0 = me;
         if (interior) {
-            code0 = dilation_dx(sx, sy, col, row);
-            pos0 = dilate(me, code0, sid, itp_b, col, row, src0);
+            code0 = dilation_code(sx, sy, col, row);
+            pos0 = dilate(me, code0, nbs[pix], itp_b, col, row, src0);
         }
         float dLdx = 0.f, dLdy = 0.f;
 #pragma unroll
@@ -550,12 +545,12 @@ __global__ void __launch_bounds__(BWD_WARPS_PER_BLOCK * 32, DIRT_BWD_MIN_BLOCKS)
             // the second group dilates to the same fragment whenever it prefers the same neighbour (the usual case):
             // the outcome of a dilation depends on the offset and on the visibility buffer only
             const float gx1 = gp[pix][3 % C] * sx1[0], gy1 = gp[pix][3 % C] * sy1[0];
-            const int code1 = interior ? dilation_dx(sx1, sy1, col, row) : 0;
+            const int code1 = interior ? dilation_code(sx1, sy1, col, row) : 0;
             if (code1 == code0) {
                 dLdx += gx1; dLdy += gy1;
             } else {
                 int src1;
-                const Fragment pos1 = dilate(me, code1, sid, itp_b, col, row, src1);
+                const Fragment pos1 = dilate(me, code1, nbs[pix], itp_b, col, row, src1);
                 if (pos1.face >= 0) {
                     if (pos1.face == pos0.face && src1 == src0) {
                         dLdx += gx1; dLdy += gy1;

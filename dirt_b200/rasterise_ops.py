@@ -70,8 +70,9 @@ def _check_shapes(op, background, vertices, vertex_colors, faces, height, width,
         raise ValueError('%s expects all arguments to have same leading (batch) dimension' % op)
 
 
-def rasterise_forward_raw(background, vertices, vertex_colors, faces, want_face_ids=True):
-    """One call of dirt_rasterise_forward on contiguous CUDA tensors. Returns (pixels, face_ids or None)."""
+def rasterise_forward_raw(background, vertices, vertex_colors, faces, want_face_ids=True, return_workspace=False):
+    """One call of dirt_rasterise_forward on contiguous CUDA tensors. Returns (pixels, face_ids or None)
+    [, workspace tensor holding the per-face setup records, reusable by rasterise_backward_raw]."""
     B, H, W, C = background.shape
     V, F = vertices.shape[1], faces.shape[1]
     pixels = torch.empty_like(background)
@@ -82,11 +83,14 @@ def rasterise_forward_raw(background, vertices, vertex_colors, faces, want_face_
                                                _ptr(pixels), _ptr(face_ids), B, H, W, C, V, F, _ptr(ws), nbytes,
                                                _stream_ptr(background.device))
     _lib.check(rc, 'Rasterise')
+    if return_workspace:
+        return pixels, face_ids, ws
     return pixels, face_ids
 
 
-def rasterise_backward_raw(vertices, faces, pixels, grad_pixels, face_ids=None, channel_groups=None):
+def rasterise_backward_raw(vertices, faces, pixels, grad_pixels, face_ids=None, channel_groups=None, setup_workspace=None):
     """One call of dirt_rasterise_backward (the RasteriseGrad op, csrc/rasterise_grad_egl.cpp:33-53).
+    `setup_workspace`: the workspace tensor of the forward call on the same (vertices, faces), if still intact.
     Returns (grad_background, grad_vertices, grad_vertex_colors)."""
     B, H, W, C = pixels.shape
     V, F = vertices.shape[1], faces.shape[1]
@@ -108,11 +112,13 @@ def rasterise_backward_raw(vertices, faces, pixels, grad_pixels, face_ids=None, 
     else:
         groups_arr = (ctypes.c_int * len(channel_groups))(*[int(g) for g in channel_groups])
         groups_ptr, n_groups = groups_arr, len(channel_groups)
-    ws, nbytes = _workspace(B, H, W, C, V, F, device)
+    nbytes = int(_lib.lib().dirt_workspace_bytes(B, H, W, C, V, F))
+    reuse = int(setup_workspace is not None and face_ids is not None and setup_workspace.numel() >= nbytes)
+    ws = setup_workspace if reuse else _workspace(B, H, W, C, V, F, device)[0]
     with torch.cuda.device(device):
         rc = _lib.lib().dirt_rasterise_backward(_ptr(vertices), _ptr(faces), _ptr(pixels), _ptr(grad_pixels), _ptr(face_ids),
                                                 _ptr(grad_background), _ptr(grad_vertices), _ptr(grad_vertex_colors),
-                                                B, H, W, C, V, F, groups_ptr, n_groups, _ptr(ws), nbytes,
+                                                B, H, W, C, V, F, groups_ptr, n_groups, reuse, _ptr(ws), nbytes,
                                                 _stream_ptr(device))
     _lib.check(rc, 'RasteriseGrad')
     return grad_background, grad_vertices, grad_vertex_colors
@@ -137,8 +143,10 @@ class _Rasterise(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, background, vertices, vertex_colors, faces, channel_groups):
-        pixels, face_ids = rasterise_forward_raw(background, vertices, vertex_colors, faces, want_face_ids=True)
+        pixels, face_ids, ws = rasterise_forward_raw(background, vertices, vertex_colors, faces, want_face_ids=True,
+                                                     return_workspace=True)
         ctx.save_for_backward(vertices, faces, pixels, face_ids)
+        ctx.setup_workspace = ws   # per-face setup records of this (vertices, faces): backward reuses them
         ctx.channel_groups = channel_groups
         ctx.mark_non_differentiable(face_ids)
         return pixels, face_ids
@@ -148,7 +156,7 @@ class _Rasterise(torch.autograd.Function):
         vertices, faces, pixels, face_ids = ctx.saved_tensors
         grad_pixels = grad_pixels.contiguous().to(torch.float32)
         grad_background, grad_vertices, grad_vertex_colors = rasterise_backward_raw(
-            vertices, faces, pixels, grad_pixels, face_ids, ctx.channel_groups)
+            vertices, faces, pixels, grad_pixels, face_ids, ctx.channel_groups, ctx.setup_workspace)
         return grad_background, grad_vertices, grad_vertex_colors, None, None  # None: wrt faces
 
 

@@ -79,6 +79,9 @@ int dirt_rasterise_forward(const float* background, const float* vertices,
  * decision and grad_vertices is summed over groups (rasterise_ops.py:163).  NULL/0 means the
  * reference's own greedy split of C.
  * face_ids may be NULL: visibility is then re-derived from (vertices, faces) inside the call.
+ * workspace_holds_setup != 0 promises that `workspace` is the buffer a preceding dirt_rasterise_forward /
+ * dirt_rasterise_visibility call on the SAME (vertices, faces, H, W) filled and that nothing has written to it
+ * since: the per-face setup records are then reused instead of recomputed (only meaningful with face_ids).
  * grad_vertices / grad_vertex_colors are zeroed by the library before accumulation;
  * grad_background is written exactly once per pixel. */
 int dirt_rasterise_backward(const float* vertices, const int32_t* faces,
@@ -86,7 +89,7 @@ int dirt_rasterise_backward(const float* vertices, const int32_t* faces,
                             const int32_t* face_ids,
                             float* grad_background, float* grad_vertices, float* grad_vertex_colors,
                             int B, int H, int W, int C, int V, int F,
-                            const int* channel_groups, int n_groups,
+                            const int* channel_groups, int n_groups, int workspace_holds_setup,
                             void* workspace, size_t workspace_bytes, void* cuda_stream);
 
 /* Debug / parity: the visibility G-buffer alone (either output may be NULL). */

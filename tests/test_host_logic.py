@@ -34,7 +34,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), name
     L = _lib.lib()
-    assert L.dirt_abi_version() == 1
+    assert L.dirt_abi_version() == 2
     assert _lib.error_string(0) == 'ok'
     assert 'workspace' in _lib.error_string(-3)
     # workspace size is a pure function of the sizes and grows with them
@@ -74,10 +74,10 @@ def test_c_abi_rejects_bad_arguments():
     assert L.dirt_rasterise_forward(null, null, null, null, null, null, 1, 0, 8, 3, 4, 2, null, 0, null) == _lib.ERR_BAD_SHAPE
     assert L.dirt_rasterise_forward(null, null, null, null, null, null, 1, 8, 8, 3, 4, 2, null, 0, null) == _lib.ERR_NULL_POINTER
     groups = (ctypes.c_int * 2)(2, 2)
-    assert L.dirt_rasterise_backward(null, null, null, null, null, null, null, null, 1, 8, 8, 4, 4, 2, groups, 2, null, 0,
+    assert L.dirt_rasterise_backward(null, null, null, null, null, null, null, null, 1, 8, 8, 4, 4, 2, groups, 2, 0, null, 0,
                                      null) == _lib.ERR_BAD_CHANNEL_GROUPS
     assert L.dirt_rasterise_backward(null, null, null, null, null, null, null, null, 1, 8, 8, 3, (1 << 24) + 1, 2, None, 0,
-                                     null, 0, null) == _lib.ERR_TOO_MANY_VERTICES
+                                     0, null, 0, null) == _lib.ERR_TOO_MANY_VERTICES
     # B == 0 is a no-op, as an empty batch is for the reference
     assert L.dirt_rasterise_forward(null, null, null, null, null, null, 0, 8, 8, 3, 4, 2, null, 0, null) == 0
 
