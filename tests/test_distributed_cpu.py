@@ -1,0 +1,58 @@
+"""CPU, world_size 2 over gloo: the host-side logic of the N > 1 path (sharding + the single all-reduce)."""
+import os
+import socket
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from dirt_b200 import distributed as dd
+
+
+def test_shard_ranges_partition_the_batch():
+    for batch in (0, 1, 7, 64, 255, 256):
+        for world in (1, 2, 3, 8):
+            ranges = [dd.shard_range(batch, r, world) for r in range(world)]
+            assert ranges[0][0] == 0 and ranges[-1][1] == batch
+            for (b0, e0), (b1, e1) in zip(ranges, ranges[1:]):
+                assert e0 == b1
+            sizes = [e - b for b, e in ranges]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(('127.0.0.1', 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, batch, V, C, out_dir):
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        g = torch.Generator().manual_seed(0)                       # identical on every rank
+        gv = torch.randn(batch, V, 4, generator=g)
+        gc = torch.randn(batch, V, C, generator=g)
+        my_gv, my_gc = dd.shard_batch([gv, gc])
+        begin, end = dd.shard_range(batch, rank, world)
+        assert my_gv.shape[0] == end - begin
+        total = dd.reduce_shared_vertex_grads(my_gv, my_gc)
+        expected = torch.cat([gv.sum(0), gc.sum(0)], dim=1)
+        np.save(os.path.join(out_dir, 'err_%d.npy' % rank), (total - expected).abs().max().numpy())
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_gloo_reduction_matches_single_process(tmp_path):
+    world, batch, V, C = 2, 7, 50, 4
+    mp.spawn(_worker, args=(world, _free_port(), batch, V, C, str(tmp_path)), nprocs=world, join=True)
+    for rank in range(world):
+        assert float(np.load(tmp_path / ('err_%d.npy' % rank))) < 1e-5
+
+
+def test_reduce_without_process_group():
+    gv, gc = torch.ones(3, 5, 4), torch.ones(3, 5, 2)
+    out = dd.reduce_shared_vertex_grads(gv, gc)
+    assert out.shape == (5, 6) and float(out.min()) == 3.0 and float(out.max()) == 3.0
