@@ -206,8 +206,12 @@ def cpu_baseline(scene, grad_pixels, sample_images, threads=None, min_seconds=10
     """fwd+bwd of the CPU oracle (a port of the reference path) on `sample_images` images of the workload,
     repeated until at least `min_seconds` of wall time have been spent (first pass untimed: page faults)."""
     from oracle import oracle
-    if threads:
-        oracle.set_threads(threads)
+    if not threads:
+        try:
+            threads = len(os.sched_getaffinity(0))
+        except AttributeError:
+            threads = os.cpu_count() or 1
+    oracle.set_threads(threads)
     n = min(sample_images, scene['background'].shape[0])
     sub = {k: np.ascontiguousarray(v[:n]) for k, v in scene.items()}
     gp = np.ascontiguousarray(grad_pixels[:n])
@@ -239,8 +243,9 @@ def run_ours(args):
     torch.cuda.set_device(local_rank)
     device = torch.device('cuda', local_rank)
     if world > 1:
+        import datetime
         import torch.distributed as dist
-        dist.init_process_group('nccl', device_id=device)
+        dist.init_process_group('nccl', device_id=device, timeout=datetime.timedelta(seconds=120))
     from dirt_b200 import build as lib_build, scenes
     if rank == 0:
         lib_build.build()
@@ -281,10 +286,11 @@ def run_ours(args):
     sync_all()
     elapsed_ms = start.elapsed_time(stop)
     # keep the GPU busy a little longer so the clock sampler sees the loaded state even for short runs
-    if sampler:
+    if sampler:   # rank 0 only: no collectives in here
         t_end = time.time() + 0.6
         while time.time() < t_end:
-            prep.step(world)
+            prep.forward()
+            prep.backward()
         torch.cuda.synchronize(device)
     clocks = sampler.finish() if sampler else None
     t = torch.tensor([elapsed_ms], dtype=torch.float64, device=device)
@@ -412,6 +418,11 @@ def run_reference(args):
     from dirt_b200 import scenes
     from oracle import oracle
     oracle.build()
+    # all the host threads this process may use (torchrun exports OMP_NUM_THREADS=1 for its workers)
+    try:
+        oracle.set_threads(len(os.sched_getaffinity(0)))
+    except AttributeError:
+        oracle.set_threads(os.cpu_count() or 1)
     gen, kwargs, desc = WORKLOADS[args.workload]
     kwargs = dict(kwargs)
     sample = min(args.cpu_sample, kwargs.get('batch', 1))
