@@ -172,34 +172,24 @@ class PreparedStep:
 
 
 class HostStep:
-    """The same two calls with HOST buffers: pinned inputs -> device, run, outputs -> pinned host."""
+    """The same two calls with HOST buffers through the package's host entry point (dirt_b200.host.HostRasteriser):
+    pinned inputs -> device, forward + backward, outputs -> pinned host, pipelined over batch chunks."""
 
-    def __init__(self, prepared):
+    def __init__(self, prepared, chunks=4):
+        from dirt_b200.host import HostRasteriser
         torch = prepared.torch
         self.p = prepared
-        self.torch = torch
+        B, H, W, C, V, F = prepared.dims
+        self.runner = HostRasteriser(B, H, W, C, V, F, device=prepared.device, chunks=chunks)
         pin = lambda a: torch.from_numpy(a).pin_memory()
         s = prepared.host
         self.h_in = dict(background=pin(s['background']), vertices=pin(s['vertices']), vertex_colors=pin(s['vertex_colors']),
                          faces=pin(s['faces']), grad_pixels=pin(prepared.grad_pixels_host))
-        self.h_out = {k: torch.empty(getattr(prepared, k).shape, dtype=getattr(prepared, k).dtype).pin_memory()
-                      for k in ('pixels', 'grad_background', 'grad_vertices', 'grad_vertex_colors')}
-        self.h2d = sum(t.numel() * t.element_size() for t in self.h_in.values())
-        self.d2h = sum(t.numel() * t.element_size() for t in self.h_out.values())
+        self.h2d = self.runner.h2d_bytes
+        self.d2h = self.runner.d2h_bytes
 
     def step(self):
-        p = self.p
-        p.background.copy_(self.h_in['background'], non_blocking=True)
-        p.vertices.copy_(self.h_in['vertices'], non_blocking=True)
-        p.vertex_colors.copy_(self.h_in['vertex_colors'], non_blocking=True)
-        p.faces.copy_(self.h_in['faces'], non_blocking=True)
-        p.forward()
-        self.h_out['pixels'].copy_(p.pixels, non_blocking=True)
-        p.grad_pixels.copy_(self.h_in['grad_pixels'], non_blocking=True)
-        p.backward()
-        self.h_out['grad_background'].copy_(p.grad_background, non_blocking=True)
-        self.h_out['grad_vertices'].copy_(p.grad_vertices, non_blocking=True)
-        self.h_out['grad_vertex_colors'].copy_(p.grad_vertex_colors, non_blocking=True)
+        return self.runner.step(**self.h_in)
 
 
 def cpu_baseline(scene, grad_pixels, sample_images, threads=None, min_seconds=10.0):

@@ -577,7 +577,7 @@ __global__ void __launch_bounds__(BWD_WARPS_PER_BLOCK * 32, DIRT_BWD_MIN_BLOCKS)
         }
     }
 
-    // ---- per-face reduction -----------------------------------------------------------------------------------
+    // ---- per-face reduction: transposed butterfly, one iteration per distinct face of the tile ---------------------
     const int owner = transposed_reduce_owner<NV>(lane);
     int last = -1;
     while (true) {
