@@ -192,6 +192,8 @@ extern "C" int dirt_rasterise_backward(const float* vertices, const int32_t* fac
     const Workspace ws = carve_workspace(workspace, B, H, W, F);
     const Dims d = make_dims(B, H, W, C, V, F);
     const int32_t* ids = face_ids;
+    // the tile coverage flags in the workspace describe `ids` when the raster kernel that produced them ran on this workspace
+    const bool flags_valid = !ids || workspace_holds_setup;
     if (!ids) {
         // no cached visibility: re-derive it exactly as the forward pass does
         CUDA_TRY(launch_setup_and_bin(vertices, faces, ws, d, stream, &launches));
@@ -201,7 +203,7 @@ extern "C" int dirt_rasterise_backward(const float* vertices, const int32_t* fac
         CUDA_TRY(launch_setup_only(vertices, faces, ws, d, stream, &launches));
     }
     CUDA_TRY(launch_backward(vertices, pixels, grad_pixels, ids, grad_background, grad_vertices, grad_vertex_colors, ws, d,
-                             groups, stream, &launches));
+                             groups, flags_valid, stream, &launches));
     t_last_launches = launches;
     return DIRT_OK;
 }

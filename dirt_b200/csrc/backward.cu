@@ -379,7 +379,7 @@ template <int C>
 __global__ void __launch_bounds__(BWD_WARPS_PER_BLOCK * 32, DIRT_BWD_MIN_BLOCKS) backward_tile_kernel(
     const float* __restrict__ vertices, const float* __restrict__ pixels, const float* __restrict__ grad_pixels,
     const int32_t* __restrict__ face_ids, float* __restrict__ grad_background, float* __restrict__ grad_vertices,
-    float* __restrict__ grad_vertex_colors, Workspace ws, Dims d)
+    float* __restrict__ grad_vertex_colors, Workspace ws, Dims d, const unsigned char* __restrict__ tile_flags)
 {
     constexpr int NS = C + 3;                  // scalars per pixel: C colour + (a,b,c)
     constexpr int NV = 3 * NS;                 // sums per face
@@ -408,14 +408,38 @@ __global__ void __launch_bounds__(BWD_WARPS_PER_BLOCK * 32, DIRT_BWD_MIN_BLOCKS)
     const size_t img = (size_t)b * H * W;
     const float halfW = 0.5f * (float)W, halfH = 0.5f * (float)H;
 
+    // ---- background-only tiles: the forward pass flagged every 16x8 tile that shows a face or touches one that does.
+    // Nothing can reach an unflagged tile: grad_background = grad_pixels and we are done.
+    if (tile_flags != nullptr && tile_flags[(size_t)b * d.tiles + ty * d.tiles_x + (tx >> 1)] == 0) {
+#pragma unroll
+        for (int pix = 0; pix < 2; ++pix) {
+            const int row = row0 + pix;
+            if (col >= W || row >= H) continue;
+            const size_t p = img + (size_t)row * W + col;
+            if (C == 4) reinterpret_cast<float4*>(grad_background)[p] = __ldg(reinterpret_cast<const float4*>(grad_pixels) + p);
+            else {
+#pragma unroll
+                for (int ch = 0; ch < C; ++ch) grad_background[p * C + ch] = __ldg(grad_pixels + p * C + ch);
+            }
+        }
+        continue;
+    }
+
     // ---- this lane's two pixels and their six outer neighbours in the visibility buffer; grad_pixels ------------
     // rows row0-1 .. row0+2 at column col, and columns col-1 / col+1 at rows row0, row0+1 (-1 outside the frame)
-    const bool col_in = col < W;
-    auto id_at = [&](int r, int c) -> int { return (r >= 0 && r < H && c >= 0 && c < W) ? __ldg(&ids[r * W + c]) : -1; };
-    const int id_up = col_in ? id_at(row0 - 1, col) : -1, id_0 = col_in ? id_at(row0, col) : -1;
-    const int id_1 = col_in ? id_at(row0 + 1, col) : -1, id_dn = col_in ? id_at(row0 + 2, col) : -1;
-    const int id_l0 = id_at(row0, col - 1), id_r0 = id_at(row0, col + 1);
-    const int id_l1 = id_at(row0 + 1, col - 1), id_r1 = id_at(row0 + 1, col + 1);
+    int id_up, id_0, id_1, id_dn, id_l0, id_r0, id_l1, id_r1;
+    if (tcol0 > 0 && trow0 > 0 && tcol0 + TILE < W && trow0 + TILE < H) {   // warp-uniform: no bounds checks needed
+        const int32_t* p0 = ids + row0 * W + col;
+        id_up = __ldg(p0 - W); id_0 = __ldg(p0); id_1 = __ldg(p0 + W); id_dn = __ldg(p0 + 2 * W);
+        id_l0 = __ldg(p0 - 1); id_r0 = __ldg(p0 + 1); id_l1 = __ldg(p0 + W - 1); id_r1 = __ldg(p0 + W + 1);
+    } else {
+        const bool col_in = col < W;
+        auto id_at = [&](int r, int c) -> int { return (r >= 0 && r < H && c >= 0 && c < W) ? __ldg(&ids[r * W + c]) : -1; };
+        id_up = col_in ? id_at(row0 - 1, col) : -1; id_0 = col_in ? id_at(row0, col) : -1;
+        id_1 = col_in ? id_at(row0 + 1, col) : -1; id_dn = col_in ? id_at(row0 + 2, col) : -1;
+        id_l0 = id_at(row0, col - 1); id_r0 = id_at(row0, col + 1);
+        id_l1 = id_at(row0 + 1, col - 1); id_r1 = id_at(row0 + 1, col + 1);
+    }
     Neighbours nbs[2];
     nbs[0].left = id_l0; nbs[0].right = id_r0; nbs[0].up = id_up; nbs[0].down = id_1;
     nbs[1].left = id_l1; nbs[1].right = id_r1; nbs[1].up = id_0; nbs[1].down = id_dn;
@@ -624,7 +648,7 @@ __global__ void __launch_bounds__(BWD_WARPS_PER_BLOCK * 32, DIRT_BWD_MIN_BLOCKS)
 cudaError_t launch_backward(const float* vertices, const float* pixels, const float* grad_pixels,
                             const int32_t* face_ids, float* grad_background, float* grad_vertices,
                             float* grad_vertex_colors, const Workspace& ws, const Dims& d, const GroupSpec& groups,
-                            cudaStream_t stream, int* launches)
+                            bool tile_flags_valid, cudaStream_t stream, int* launches)
 {
     cudaError_t e;
     if ((e = cudaMemsetAsync(grad_vertices, 0, sizeof(float) * (size_t)d.B * d.V * 4, stream)) != cudaSuccess) return e;
@@ -637,17 +661,18 @@ cudaError_t launch_backward(const float* vertices, const float* pixels, const fl
                                 (d.C == 4 && groups.n == 2 && groups.width[0] == 3 && groups.width[1] == 1);
     const bool aligned4 = d.C != 4 || (((uintptr_t)pixels | (uintptr_t)grad_pixels | (uintptr_t)grad_background) % 16 == 0);
     const dim3 block(BWD_WARPS_PER_BLOCK * 32);
+    const unsigned char* flags = tile_flags_valid ? ws.tile_flags : nullptr;
     const dim3 grid2((unsigned)((d.btiles_x + BWD_WARPS_PER_BLOCK - 1) / BWD_WARPS_PER_BLOCK), (unsigned)d.btiles_y,
                      (unsigned)min(d.B, 65535));
     if (default_groups && aligned4 && d.C == 4)
         backward_tile_kernel<4><<<grid2, block, 0, stream>>>(vertices, pixels, grad_pixels, face_ids, grad_background,
-                                                             grad_vertices, grad_vertex_colors, ws, d);
+                                                             grad_vertices, grad_vertex_colors, ws, d, flags);
     else if (default_groups && d.C == 3)
         backward_tile_kernel<3><<<grid2, block, 0, stream>>>(vertices, pixels, grad_pixels, face_ids, grad_background,
-                                                             grad_vertices, grad_vertex_colors, ws, d);
+                                                             grad_vertices, grad_vertex_colors, ws, d, flags);
     else if (default_groups && d.C == 1)
         backward_tile_kernel<1><<<grid2, block, 0, stream>>>(vertices, pixels, grad_pixels, face_ids, grad_background,
-                                                             grad_vertices, grad_vertex_colors, ws, d);
+                                                             grad_vertices, grad_vertex_colors, ws, d, flags);
     else {
         const unsigned grid = (unsigned)((total_tiles + BWD_WARPS_PER_BLOCK - 1) / BWD_WARPS_PER_BLOCK);
         backward_generic_kernel<<<grid, block, 0, stream>>>(vertices, pixels, grad_pixels, face_ids, grad_background,

@@ -55,6 +55,7 @@ struct Workspace {
     TriInterp* itp;       // [B*F]
     uint2* tri_bin;       // [B*F]  tile bbox (tx0|ty0<<16, tx1|ty1<<16); x = 0xFFFFFFFF: not binned per tile
     int* tile_count;      // [B*T]  per-tile reference count, then reused as the fill cursor
+    unsigned char* tile_flags;  // [B*T]  1 if the 16x8 tile or one of its 8 neighbours shows a face (written by the raster kernel)
     int2* tile_range;     // [B*T]  (offset into refs, count)
     int* large_count;     // [B]
     int* large_list;      // [B*F]
@@ -78,6 +79,7 @@ inline Workspace carve_workspace(void* base, int B, int H, int W, int F)
     ws.itp = (TriInterp*)take(BF * sizeof(TriInterp));
     ws.tri_bin = (uint2*)take(BF * sizeof(uint2));
     ws.tile_count = (int*)take(BT * sizeof(int));
+    ws.tile_flags = (unsigned char*)take(BT);
     ws.tile_range = (int2*)take(BT * sizeof(int2));
     ws.large_count = (int*)take((size_t)B * sizeof(int));
     ws.large_list = (int*)take(BF * sizeof(int));
@@ -260,6 +262,6 @@ cudaError_t launch_raster_visibility(const float* vertices, int32_t* face_ids, f
 cudaError_t launch_backward(const float* vertices, const float* pixels, const float* grad_pixels,
                             const int32_t* face_ids, float* grad_background, float* grad_vertices,
                             float* grad_vertex_colors, const Workspace& ws, const Dims& d, const GroupSpec& groups,
-                            cudaStream_t stream, int* launches);
+                            bool tile_flags_valid, cudaStream_t stream, int* launches);
 
 }  // namespace dirt

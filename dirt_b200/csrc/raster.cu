@@ -258,6 +258,17 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, DIRT_RASTER_MIN_BLOCKS) 
         consume_list<false>(ws.large_list + (size_t)b * d.F, nlarge, cov_b, itp_b, verts, slots_all[warp], lane, tcol0,
                             trow0, d.H, d.W, quad, tile_max);
 
+    // tile coverage flags for the backward pass: a tile that shows any face marks itself and its 8 neighbours
+    // (the backward pass reaches one pixel beyond its own tile)
+    {
+        const bool any_cov = __any_sync(0xffffffffu, ((uint32_t)(quad.best[0] >> 32) < KEY_EMPTY) | ((uint32_t)(quad.best[1] >> 32) < KEY_EMPTY) |
+                                                     ((uint32_t)(quad.best[2] >> 32) < KEY_EMPTY) | ((uint32_t)(quad.best[3] >> 32) < KEY_EMPTY));
+        if (any_cov && lane < 9) {
+            const int nx = tx + (lane % 3) - 1, ny = ty + (lane / 3) - 1;
+            if (nx >= 0 && nx < d.tiles_x && ny >= 0 && ny < d.tiles_y) ws.tile_flags[(size_t)b * d.tiles + ny * d.tiles_x + nx] = 1;
+        }
+    }
+
     const int col0 = tcol0 + (lane & 7) * 2, row0 = trow0 + (lane >> 3) * 2;
     const int C = (CT > 0) ? CT : d.C;
     const float* cols = vertex_colors + (size_t)b * d.V * C;
