@@ -11,6 +11,9 @@
 namespace dirt {
 
 constexpr int BWD_WARPS_PER_BLOCK = 4;
+#ifndef DIRT_BWD_GROUP
+#define DIRT_BWD_GROUP 32   // lanes per reduction strip; 32 = one face at a time over the whole warp (measured best: profiles/r01_sweep_group.txt)
+#endif
 #ifndef DIRT_BWD_MIN_BLOCKS
 #define DIRT_BWD_MIN_BLOCKS 8   // <= 64 registers: measured best (profiles/r01_sweep_bounds.txt)
 #endif
@@ -326,11 +329,14 @@ __device__ __forceinline__ void scharr_global(const float* __restrict__ pixels, 
     sy[2] = scharr_comp(a_mm.z, a_pm.z, a_mp.z, a_pp.z, a_0m.z, a_0p.z);
 }
 
-template <int N>
+// Transposed butterfly over the lanes that differ in bits `bit`, bit/2, ..., 1: at every step a lane keeps half of its
+// sums and hands the other half to its partner.  After STEPS steps each lane is left with OUT = ceil(N / 2^STEPS) sums.
+template <int N, int STEPS>
 struct TransposedReduce {
-    static __device__ __forceinline__ float run(float (&v)[N], int lane, int bit)
+    static constexpr int H = (N + 1) / 2;
+    static constexpr int OUT = TransposedReduce<H, STEPS - 1>::OUT;
+    static __device__ __forceinline__ void run(float (&v)[N], int lane, int bit, float (&out)[OUT])
     {
-        constexpr int H = (N + 1) / 2;
         float w[H];
         const bool up = (lane & bit) != 0;
 #pragma unroll
@@ -340,40 +346,31 @@ struct TransposedReduce {
             const float keep = up ? hi : v[i];
             w[i] = keep + __shfl_xor_sync(0xffffffffu, send, bit);
         }
-        return TransposedReduce<H>::run(w, lane, bit >> 1);
+        TransposedReduce<H, STEPS - 1>::run(w, lane, bit >> 1, out);
     }
-};
-template <>
-struct TransposedReduce<1> {
-    static __device__ __forceinline__ float run(float (&v)[1], int, int bit)
+    // global index of out[0] on this lane: out[i] is sum base+i (entries beyond the valid range are padding)
+    static __device__ __forceinline__ int base(int lane, int bit)
     {
-        float x = v[0];
-        for (; bit; bit >>= 1) x += __shfl_xor_sync(0xffffffffu, x, bit);
-        return x;
+        return ((lane & bit) ? H : 0) + TransposedReduce<H, STEPS - 1>::base(lane, bit >> 1);
+    }
+    // is out[i] a real sum?  (checks the padding introduced at every level)
+    static __device__ __forceinline__ bool valid(int lane, int bit, int i)
+    {
+        const int p = TransposedReduce<H, STEPS - 1>::base(lane, bit >> 1) + i;   // position inside this level's kept half
+        return TransposedReduce<H, STEPS - 1>::valid(lane, bit >> 1, i) && (((lane & bit) ? H : 0) + p < N);
     }
 };
-
-// which of the N sums this lane owns after TransposedReduce<N> (-1: none)
 template <int N>
-__device__ __forceinline__ int transposed_reduce_owner(int lane)
-{
-    int sizes[6];
-    int n = N, steps = 0;
-    for (int bit = 16; bit && n > 1; bit >>= 1) { sizes[steps++] = n; n = (n + 1) / 2; }
-    if (steps == 0) return lane == 0 ? 0 : -1;
-    int p = 0;
-    bool valid = true;
-    for (int s = steps - 1; s >= 0; --s) {
-        const int bit = 16 >> s;
-        const int h = (sizes[s] + 1) / 2;
-        p += (lane & bit) ? h : 0;
-        valid = valid && (p < sizes[s]);
+struct TransposedReduce<N, 0> {
+    static constexpr int OUT = N;
+    static __device__ __forceinline__ void run(float (&v)[N], int, int, float (&out)[N])
+    {
+#pragma unroll
+        for (int i = 0; i < N; ++i) out[i] = v[i];
     }
-    // lanes that differ only in the unused low bits all hold the same (fully reduced) sum: let one write
-    const int unused = (16 >> (steps - 1)) - 1;
-    if (lane & unused) valid = false;
-    return valid ? p : -1;
-}
+    static __device__ __forceinline__ int base(int, int) { return 0; }
+    static __device__ __forceinline__ bool valid(int, int, int i) { return i < N; }
+};
 
 template <int C>
 __global__ void __launch_bounds__(BWD_WARPS_PER_BLOCK * 32, DIRT_BWD_MIN_BLOCKS) backward_tile_kernel(
@@ -601,45 +598,66 @@ __global__ void __launch_bounds__(BWD_WARPS_PER_BLOCK * 32, DIRT_BWD_MIN_BLOCKS)
         }
     }
 
-    // ---- per-face reduction: transposed butterfly, one iteration per distinct face of the tile ---------------------
-    const int owner = transposed_reduce_owner<NV>(lane);
-    int last = -1;
-    while (true) {
-        // next distinct face key greater than `last`
-        unsigned cand = 0x7fffffffu;
+    // ---- per-face reduction -------------------------------------------------------------------------------------
+    // The warp is cut into strips of GROUP lanes (GROUP = 8: two tile rows).  Every strip walks ITS OWN distinct faces
+    // (REDUX.MIN restricted to the strip) and reduces the 3*(C+3) sums of the current face over its lanes with a
+    // transposed butterfly of log2(GROUP) steps, so the strips work on different faces at the same time; each lane ends
+    // up with ceil(NV/GROUP) finished sums and adds them to global memory (RED).  The L2 atomic units are almost idle
+    // on this kernel (profiles/): trading a few more REDs for far fewer shuffle rounds pays.
+    {
+        constexpr int GROUP = DIRT_BWD_GROUP;
+        constexpr int STEPS = (GROUP == 32) ? 5 : (GROUP == 16) ? 4 : (GROUP == 8) ? 3 : (GROUP == 4) ? 2 : 1;
+        using Red = TransposedReduce<NV, STEPS>;
+        constexpr int OUT = Red::OUT;
+        const unsigned group_mask = (GROUP == 32) ? 0xffffffffu : (((1u << (GROUP & 31)) - 1u) << (lane & ~(GROUP - 1)));
+        const int top_bit = GROUP >> 1;
+        const int out_base = Red::base(lane, top_bit);
+        int last = -1;
+        while (true) {
+            // next distinct face key of this strip greater than `last`
+            unsigned cand = 0x7fffffffu;
 #pragma unroll
-        for (int pix = 0; pix < 2; ++pix) {
-            if (term[pix].key_col > last) cand = min(cand, (unsigned)term[pix].key_col);
-            if (term[pix].key_pos > last) cand = min(cand, (unsigned)term[pix].key_pos);
-        }
-        const unsigned fmin = __reduce_min_sync(0xffffffffu, cand);
-        if (fmin == 0x7fffffffu) break;
-        const int f = (int)fmin;
-        last = f;
+            for (int pix = 0; pix < 2; ++pix) {
+                if (term[pix].key_col > last) cand = min(cand, (unsigned)term[pix].key_col);
+                if (term[pix].key_pos > last) cand = min(cand, (unsigned)term[pix].key_pos);
+            }
+            const unsigned fmin = __reduce_min_sync(group_mask, cand);
+            if (!__any_sync(0xffffffffu, fmin != 0x7fffffffu)) break;   // every strip is done
+            const bool active = fmin != 0x7fffffffu;
+            const int f = active ? (int)fmin : -1;
+            if (active) last = f;
 
-        float v[NV];
+            float v[NV];
 #pragma unroll
-        for (int pix = 0; pix < 2; ++pix) {
-            const PixelTerms& T = term[pix];
-            const bool mc = T.key_col == f, mp = T.key_pos == f;
-            const float wc[3] = {mc ? T.bc0 : 0.f, mc ? T.bc1 : 0.f, mc ? T.bc2 : 0.f};
-            const float wp[3] = {mp ? T.bp0 : 0.f, mp ? T.bp1 : 0.f, mp ? T.bp2 : 0.f};
+            for (int pix = 0; pix < 2; ++pix) {
+                const PixelTerms& T = term[pix];
+                const bool mc = active && T.key_col == f, mp = active && T.key_pos == f;
+                const float wc[3] = {mc ? T.bc0 : 0.f, mc ? T.bc1 : 0.f, mc ? T.bc2 : 0.f};
+                const float wp[3] = {mp ? T.bp0 : 0.f, mp ? T.bp1 : 0.f, mp ? T.bp2 : 0.f};
 #pragma unroll
-            for (int k = 0; k < 3; ++k) {
+                for (int k = 0; k < 3; ++k) {
 #pragma unroll
-                for (int j = 0; j < NS; ++j) {
-                    const float w = (j < C) ? wc[k] : wp[k];
-                    v[k * NS + j] = (pix == 0) ? w * sc[pix][j] : fmaf(w, sc[pix][j], v[k * NS + j]);
+                    for (int j = 0; j < NS; ++j) {
+                        const float w = (j < C) ? wc[k] : wp[k];
+                        v[k * NS + j] = (pix == 0) ? w * sc[pix][j] : fmaf(w, sc[pix][j], v[k * NS + j]);
+                    }
                 }
             }
-        }
-        const float total = TransposedReduce<NV>::run(v, lane, 16);
-        if (owner >= 0) {
-            const int k = owner / NS, j = owner - k * NS;
-            const int4 q = __ldg(reinterpret_cast<const int4*>(itp_b + f) + 2);   // {sC, v0, v1, v2}
-            const int vid = (k == 0) ? q.y : (k == 1) ? q.z : q.w;
-            float* dst = (j < C) ? (gcols + (size_t)vid * C + j) : (gverts + (size_t)vid * 4 + (j - C == 2 ? 3 : j - C));
-            atomicAdd(dst, total);
+            float out[OUT];
+            Red::run(v, lane, top_bit, out);
+            if (active) {
+                const int4 q = __ldg(reinterpret_cast<const int4*>(itp_b + f) + 2);   // {sC, v0, v1, v2}
+#pragma unroll
+                for (int i = 0; i < OUT; ++i) {
+                    const int idx = out_base + i;
+                    if (Red::valid(lane, top_bit, i)) {
+                        const int k = idx / NS, j = idx - k * NS;
+                        const int vid = (k == 0) ? q.y : (k == 1) ? q.z : q.w;
+                        float* dst = (j < C) ? (gcols + (size_t)vid * C + j) : (gverts + (size_t)vid * 4 + (j - C == 2 ? 3 : j - C));
+                        atomicAdd(dst, out[i]);
+                    }
+                }
+            }
         }
     }
     }
