@@ -556,7 +556,7 @@ __global__ void __launch_bounds__(BWD_WARPS_PER_BLOCK * 32, DIRT_BWD_MIN_BLOCKS)
             const float2 p2 = __ldg(reinterpret_cast<const float2*>(verts + (size_t)fr.v2 * 4));
             const float clip_x = fr.g.x * p0.x + fr.g.y * p1.x + fr.g.z * p2.x;
             const float clip_y = fr.g.x * p0.y + fr.g.y * p1.y + fr.g.z * p2.y;
-            const float inv_w = __frcp_rn(fr.g.w);
+            const float inv_w = __fdividef(1.0f, fr.g.w);
             a = gx * halfW * inv_w;
             bb = gy * halfH * inv_w;
             cc = -(a * clip_x + bb * clip_y) * inv_w;

@@ -171,12 +171,28 @@ __device__ __forceinline__ double plane_double(const double g[3], int col, int r
     return __dadd_rn(__dmul_rn(g[0], (double)col), __dadd_rn(__dmul_rn(g[1], (double)row), g[2]));
 }
 
+// Correctly rounded 1/x without the subroutine call __frcp_rn compiles to: MUFU.RCP (<= 1 ulp) followed by one
+// fused Newton step is correctly rounded for every x whose reciprocal is a normal number; the rare remaining
+// magnitudes take the library path.  (tests/test_gpu_parity.py::test_visibility_gbuffer_matches_oracle compares the
+// result bit for bit with the oracle's IEEE 1.0f / x.)
+__device__ __forceinline__ float rcp_rn(float x)
+{
+    const float ax = fabsf(x);
+    if (ax > 1.0e-30f && ax < 1.0e30f) {
+        float r;
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+        const float e = __fmaf_rn(-x, r, 1.0f);
+        return __fmaf_rn(r, e, r);
+    }
+    return __frcp_rn(x);
+}
+
 // G: barycentrics and clip-w of a face at pixel (col,row)
 __device__ __forceinline__ float4 gbuffer_at(const TriInterp& t, int col, int row)
 {
     const float dc = (float)(col - t.cref), dr = (float)(row - t.rref);
     const float S = __fmaf_rn(t.sA, dc, __fmaf_rn(t.sB, dr, t.sC));
-    const float cw = __frcp_rn(S);   // correctly rounded reciprocal == the oracle's IEEE 1.0f / S
+    const float cw = rcp_rn(S);   // correctly rounded reciprocal == the oracle's IEEE 1.0f / S
     const float q0 = __fmaf_rn(t.q0A, dc, __fmaf_rn(t.q0B, dr, t.q0C));
     const float q1 = __fmaf_rn(t.q1A, dc, __fmaf_rn(t.q1B, dr, t.q1C));
     const float b0 = __fmul_rn(q0, cw), b1 = __fmul_rn(q1, cw);

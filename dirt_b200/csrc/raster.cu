@@ -200,7 +200,7 @@ __device__ __forceinline__ void shade_pixel(const TriInterp& ti, int col, int ro
     // (tests/square_test.py).  Values only, no decision depends on them.
     const float dc = (float)(col - ti.cref), dr = (float)(row - ti.rref);
     const float S = fmaf(ti.sA, dc, fmaf(ti.sB, dr, ti.sC));
-    const float cw = __frcp_rn(S);
+    const float cw = __fdividef(1.0f, S);
     const float b0 = fmaf(ti.q0A, dc, fmaf(ti.q0B, dr, ti.q0C)) * cw;
     const float b1 = fmaf(ti.q1A, dc, fmaf(ti.q1B, dr, ti.q1C)) * cw;
     if (CT == 4) {
