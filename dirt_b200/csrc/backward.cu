@@ -234,7 +234,7 @@ __device__ __forceinline__ int dilation_code(const float (&sx)[3], const float (
 
 struct Neighbours { int left, right, up, down; };   // face ids at (col-1,row), (col+1,row), (col,row-1), (col,row+1)
 
-__device__ __forceinline__ Fragment dilate(const Fragment& own, int code, const Neighbours& nb,
+__device__ __forceinline__ Fragment dilate(const Fragment& own, int code, const Neighbours nb,
                                            const TriInterp* __restrict__ itp_b, int col, int row, int& src)
 {
     src = 0;
@@ -437,9 +437,8 @@ __global__ void __launch_bounds__(BWD_WARPS_PER_BLOCK * 32, DIRT_BWD_MIN_BLOCKS)
         id_l0 = id_at(row0, col - 1); id_r0 = id_at(row0, col + 1);
         id_l1 = id_at(row0 + 1, col - 1); id_r1 = id_at(row0 + 1, col + 1);
     }
-    Neighbours nbs[2];
-    nbs[0].left = id_l0; nbs[0].right = id_r0; nbs[0].up = id_up; nbs[0].down = id_1;
-    nbs[1].left = id_l1; nbs[1].right = id_r1; nbs[1].up = id_0; nbs[1].down = id_dn;
+    const Neighbours nb0 = {id_l0, id_r0, id_up, id_1};
+    const Neighbours nb1 = {id_l1, id_r1, id_0, id_dn};
     float gp[2][C];
 #pragma unroll
     for (int pix = 0; pix < 2; ++pix) {
@@ -478,7 +477,7 @@ __global__ void __launch_bounds__(BWD_WARPS_PER_BLOCK * 32, DIRT_BWD_MIN_BLOCKS)
         // own coverage, or (interior pixels only) a covered 4-neighbour that could dilate into this pixel
         bool n = f >= 0;
         if (!n && col > 0 && row > 0 && col < W - 1 && row < H - 1)
-            n = (nbs[pix].left & nbs[pix].right & nbs[pix].up & nbs[pix].down) >= 0;   // any of the four non-negative
+            n = pix ? ((nb1.left & nb1.right & nb1.up & nb1.down) >= 0) : ((nb0.left & nb0.right & nb0.up & nb0.down) >= 0);   // any of the four non-negative
         if (n) f_own[pix] = f;   // -2: nothing can reach this pixel
         near = near || n;
     }
@@ -543,7 +542,7 @@ __global__ void __launch_bounds__(BWD_WARPS_PER_BLOCK * 32, DIRT_BWD_MIN_BLOCKS)
         Fragment pos0 = me;
         if (interior) {
             code0 = dilation_code(sx, sy, col, row);
-            pos0 = dilate(me, code0, nbs[pix], itp_b, col, row, src0);
+            pos0 = dilate(me, code0, pix ? nb1 : nb0, itp_b, col, row, src0);
         }
         float dLdx = 0.f, dLdy = 0.f;
 #pragma unroll
@@ -571,7 +570,7 @@ __global__ void __launch_bounds__(BWD_WARPS_PER_BLOCK * 32, DIRT_BWD_MIN_BLOCKS)
                 dLdx += gx1; dLdy += gy1;
             } else {
                 int src1;
-                const Fragment pos1 = dilate(me, code1, nbs[pix], itp_b, col, row, src1);
+                const Fragment pos1 = dilate(me, code1, pix ? nb1 : nb0, itp_b, col, row, src1);
                 if (pos1.face >= 0) {
                     if (pos1.face == pos0.face && src1 == src0) {
                         dLdx += gx1; dLdy += gy1;
