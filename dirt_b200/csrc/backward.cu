@@ -10,9 +10,15 @@
 
 namespace dirt {
 
-constexpr int BWD_WARPS_PER_BLOCK = 4;
-#ifndef DIRT_BWD_GROUP
-#define DIRT_BWD_GROUP 32   // lanes per reduction strip; 32 = one face at a time over the whole warp (measured best: profiles/r01_sweep_group.txt)
+#ifndef DIRT_BWD_WARPS
+#define DIRT_BWD_WARPS 4
+#endif
+constexpr int BWD_WARPS_PER_BLOCK = DIRT_BWD_WARPS;
+#ifndef DIRT_ABLATE
+#define DIRT_ABLATE 0   // timing experiments only: 1 = no per-face reduction, 2 = no Scharr/dilation, 3 = both
+#endif
+#ifndef DIRT_BWD_SMALL_FACE
+#define DIRT_BWD_SMALL_FACE 12  // faces owning at most this many records in a tile are added directly (0: always reduce); profiles/r01_sweep_small_face.txt
 #endif
 #ifndef DIRT_BWD_MIN_BLOCKS
 #define DIRT_BWD_MIN_BLOCKS 8   // <= 64 registers: measured best (profiles/r01_sweep_bounds.txt)
@@ -193,6 +199,12 @@ __global__ void __launch_bounds__(BWD_WARPS_PER_BLOCK * 32) backward_generic_ker
 
 constexpr int HALO_ROWS = TILE + 2;   // 10
 constexpr int HALO_COLS = TILE + 4;   // 12: col-1 .. col+10
+
+// 16-byte vector reduction to global memory (sm_90+): four fp32 adds in one RED
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d)
+{
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
 
 struct PixelTerms {      // everything one pixel contributes (fast path)
     int key_col;         // own face (-1: uncovered)
@@ -529,6 +541,11 @@ __global__ void __launch_bounds__(BWD_WARPS_PER_BLOCK * 32, DIRT_BWD_MIN_BLOCKS)
         const bool interior = col > 0 && row > 0 && col < W - 1 && row < H - 1;
         T.key_col = me.face;
         if (me.face >= 0) { T.bc0 = me.g.x; T.bc1 = me.g.y; T.bc2 = me.g.z; }
+#if DIRT_ABLATE >= 2
+        T.key_pos = me.face; T.bp0 = T.bc0; T.bp1 = T.bc1; T.bp2 = T.bc2;
+        sc[pix][C] = gp[pix][0]; sc[pix][C + 1] = gp[pix][0]; sc[pix][C + 2] = gp[pix][0];
+        continue;
+#endif
 
         float sx[3], sy[3], sx1[3], sy1[3];
         if (staged) {
@@ -598,39 +615,42 @@ __global__ void __launch_bounds__(BWD_WARPS_PER_BLOCK * 32, DIRT_BWD_MIN_BLOCKS)
     }
 
     // ---- per-face reduction -------------------------------------------------------------------------------------
-    // The warp is cut into strips of GROUP lanes (GROUP = 8: two tile rows).  Every strip walks ITS OWN distinct faces
-    // (REDUX.MIN restricted to the strip) and reduces the 3*(C+3) sums of the current face over its lanes with a
-    // transposed butterfly of log2(GROUP) steps, so the strips work on different faces at the same time; each lane ends
-    // up with ceil(NV/GROUP) finished sums and adds them to global memory (RED).  The L2 atomic units are almost idle
-    // on this kernel (profiles/): trading a few more REDs for far fewer shuffle rounds pays.
+    // One iteration per distinct face of the tile (REDUX.MIN over the keys): the 3*(C+3) sums of the face are reduced
+    // over the 32 lanes with a transposed butterfly (each lane ends up owning one finished sum) and leave the SM as ONE
+    // warp-wide RED.  Faces that own only a few records in this tile skip the butterfly: their records are added
+    // directly, all such faces of the tile together, in one pass of vector REDs at the end.
+#if DIRT_ABLATE != 1
     {
-        constexpr int GROUP = DIRT_BWD_GROUP;
-        constexpr int STEPS = (GROUP == 32) ? 5 : (GROUP == 16) ? 4 : (GROUP == 8) ? 3 : (GROUP == 4) ? 2 : 1;
-        using Red = TransposedReduce<NV, STEPS>;
-        constexpr int OUT = Red::OUT;
-        const unsigned group_mask = (GROUP == 32) ? 0xffffffffu : (((1u << (GROUP & 31)) - 1u) << (lane & ~(GROUP - 1)));
-        const int top_bit = GROUP >> 1;
-        const int out_base = Red::base(lane, top_bit);
+        using Red = TransposedReduce<NV, 5>;
+        const int owner = Red::valid(lane, 16, 0) ? Red::base(lane, 16) : -1;
+        const int kc0 = term[0].key_col, kc1 = term[1].key_col, kp0 = term[0].key_pos, kp1 = term[1].key_pos;
+        unsigned direct = 0;   // bit 0/1: colour record of pixel 0/1, bit 2/3: position record of pixel 0/1
         int last = -1;
         while (true) {
-            // next distinct face key of this strip greater than `last`
+            // next distinct face key greater than `last`
             unsigned cand = 0x7fffffffu;
-#pragma unroll
-            for (int pix = 0; pix < 2; ++pix) {
-                if (term[pix].key_col > last) cand = min(cand, (unsigned)term[pix].key_col);
-                if (term[pix].key_pos > last) cand = min(cand, (unsigned)term[pix].key_pos);
+            if (kc0 > last) cand = min(cand, (unsigned)kc0);
+            if (kc1 > last) cand = min(cand, (unsigned)kc1);
+            if (kp0 > last) cand = min(cand, (unsigned)kp0);
+            if (kp1 > last) cand = min(cand, (unsigned)kp1);
+            const unsigned fmin = __reduce_min_sync(0xffffffffu, cand);
+            if (fmin == 0x7fffffffu) break;
+            const int f = (int)fmin;
+            last = f;
+            const bool mc0 = kc0 == f, mc1 = kc1 == f, mp0 = kp0 == f, mp1 = kp1 == f;
+#if DIRT_BWD_SMALL_FACE > 0
+            const int records = __popc(__ballot_sync(0xffffffffu, mc0)) + __popc(__ballot_sync(0xffffffffu, mc1)) +
+                                __popc(__ballot_sync(0xffffffffu, mp0)) + __popc(__ballot_sync(0xffffffffu, mp1));
+            if (records <= DIRT_BWD_SMALL_FACE) {
+                direct |= (mc0 ? 1u : 0u) | (mc1 ? 2u : 0u) | (mp0 ? 4u : 0u) | (mp1 ? 8u : 0u);
+                continue;
             }
-            const unsigned fmin = __reduce_min_sync(group_mask, cand);
-            if (!__any_sync(0xffffffffu, fmin != 0x7fffffffu)) break;   // every strip is done
-            const bool active = fmin != 0x7fffffffu;
-            const int f = active ? (int)fmin : -1;
-            if (active) last = f;
-
+#endif
             float v[NV];
 #pragma unroll
             for (int pix = 0; pix < 2; ++pix) {
                 const PixelTerms& T = term[pix];
-                const bool mc = active && T.key_col == f, mp = active && T.key_pos == f;
+                const bool mc = pix ? mc1 : mc0, mp = pix ? mp1 : mp0;
                 const float wc[3] = {mc ? T.bc0 : 0.f, mc ? T.bc1 : 0.f, mc ? T.bc2 : 0.f};
                 const float wp[3] = {mp ? T.bp0 : 0.f, mp ? T.bp1 : 0.f, mp ? T.bp2 : 0.f};
 #pragma unroll
@@ -642,23 +662,45 @@ __global__ void __launch_bounds__(BWD_WARPS_PER_BLOCK * 32, DIRT_BWD_MIN_BLOCKS)
                     }
                 }
             }
-            float out[OUT];
-            Red::run(v, lane, top_bit, out);
-            if (active) {
+            float total[1];
+            Red::run(v, lane, 16, total);
+            if (owner >= 0) {
+                const int k = owner / NS, j = owner - k * NS;
                 const int4 q = __ldg(reinterpret_cast<const int4*>(itp_b + f) + 2);   // {sC, v0, v1, v2}
+                const int vid = (k == 0) ? q.y : (k == 1) ? q.z : q.w;
+                float* dst = (j < C) ? (gcols + (size_t)vid * C + j) : (gverts + (size_t)vid * 4 + (j - C == 2 ? 3 : j - C));
+                atomicAdd(dst, total[0]);
+            }
+        }
+#if DIRT_BWD_SMALL_FACE > 0
+        if (__any_sync(0xffffffffu, direct != 0u)) {
 #pragma unroll
-                for (int i = 0; i < OUT; ++i) {
-                    const int idx = out_base + i;
-                    if (Red::valid(lane, top_bit, i)) {
-                        const int k = idx / NS, j = idx - k * NS;
-                        const int vid = (k == 0) ? q.y : (k == 1) ? q.z : q.w;
-                        float* dst = (j < C) ? (gcols + (size_t)vid * C + j) : (gverts + (size_t)vid * 4 + (j - C == 2 ? 3 : j - C));
-                        atomicAdd(dst, out[i]);
+            for (int rec = 0; rec < 4; ++rec) {
+                if (!(direct & (1u << rec))) continue;
+                const int pix = rec & 1;
+                const PixelTerms& T = term[pix];
+                const bool colour = rec < 2;
+                const int f = colour ? T.key_col : T.key_pos;
+                const int4 q = __ldg(reinterpret_cast<const int4*>(itp_b + f) + 2);
+                const int vid[3] = {q.y, q.z, q.w};
+                const float w[3] = {colour ? T.bc0 : T.bp0, colour ? T.bc1 : T.bp1, colour ? T.bc2 : T.bp2};
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    if (colour) {
+                        if (C == 4) red_add_v4(gcols + (size_t)vid[k] * 4, w[k] * sc[pix][0], w[k] * sc[pix][1 % NS], w[k] * sc[pix][2 % NS], w[k] * sc[pix][3 % NS]);
+                        else {
+#pragma unroll
+                            for (int j = 0; j < C; ++j) atomicAdd(gcols + (size_t)vid[k] * C + j, w[k] * sc[pix][j]);
+                        }
+                    } else {
+                        red_add_v4(gverts + (size_t)vid[k] * 4, w[k] * sc[pix][C], w[k] * sc[pix][C + 1], 0.f, w[k] * sc[pix][C + 2]);
                     }
                 }
             }
         }
+#endif
     }
+#endif
     }
 }
 
@@ -676,7 +718,8 @@ cudaError_t launch_backward(const float* vertices, const float* pixels, const fl
     // fast path: the reference's default grouping of C in {1,3,4}; pointers vector-aligned where the kernel needs it
     const bool default_groups = (d.C == 1 && groups.n == 1) || (d.C == 3 && groups.n == 1 && groups.width[0] == 3) ||
                                 (d.C == 4 && groups.n == 2 && groups.width[0] == 3 && groups.width[1] == 1);
-    const bool aligned4 = d.C != 4 || (((uintptr_t)pixels | (uintptr_t)grad_pixels | (uintptr_t)grad_background) % 16 == 0);
+    const bool aligned4 = d.C != 4 || (((uintptr_t)pixels | (uintptr_t)grad_pixels | (uintptr_t)grad_background |
+                                        (uintptr_t)grad_vertex_colors) % 16 == 0);
     const dim3 block(BWD_WARPS_PER_BLOCK * 32);
     const unsigned char* flags = tile_flags_valid ? ws.tile_flags : nullptr;
     const dim3 grid2((unsigned)((d.btiles_x + BWD_WARPS_PER_BLOCK - 1) / BWD_WARPS_PER_BLOCK), (unsigned)d.btiles_y,

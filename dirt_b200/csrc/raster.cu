@@ -20,7 +20,10 @@
 
 namespace dirt {
 
-constexpr int WARPS_PER_BLOCK = 4;
+#ifndef DIRT_RASTER_WARPS
+#define DIRT_RASTER_WARPS 4
+#endif
+constexpr int WARPS_PER_BLOCK = DIRT_RASTER_WARPS;
 #ifndef DIRT_RASTER_MIN_BLOCKS
 #define DIRT_RASTER_MIN_BLOCKS 8   // <= 64 registers: measured best (profiles/r01_sweep_bounds.txt)
 #endif
