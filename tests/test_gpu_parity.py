@@ -222,3 +222,75 @@ def test_host_entry_point_matches_oracle(cuda_lib, oracle):
     np.testing.assert_array_equal(out['grad_background'].numpy(), gb_o)
     assert rel_close(out['grad_vertices'].numpy(), gv_o)[0]
     assert rel_close(out['grad_vertex_colors'].numpy(), gc_o)[0]
+
+
+@pytest.mark.parametrize('channels,groups', [(3, [1, 1, 1]), (4, [1, 3]), (4, [1, 1, 1, 1]), (6, [3, 3])])
+def test_custom_channel_groups(cuda_lib, oracle, channels, groups):
+    # any grouping into widths 1 and 3 is a valid RasteriseGrad call sequence (dirt/rasterise_ops.py:132-177);
+    # non-default groupings take the generic backward kernel
+    s = scenes.bent_square_scene(40, 32, channels=channels, seed=3)
+    pixels_o = oracle.forward(**s)
+    gp = np.random.default_rng(1).standard_normal(pixels_o.shape).astype(np.float32)
+    gb_o, gv_o, gc_o = oracle.backward(s['vertices'], s['faces'], pixels_o, gp, groups)
+    gb_g, gv_g, gc_g = _backward(s, pixels_o, gp, None, groups)
+    np.testing.assert_array_equal(gb_g, gb_o)
+    assert rel_close(gv_g, gv_o)[0] and rel_close(gc_g, gc_o)[0]
+    with pytest.raises(ValueError):
+        _backward(s, pixels_o, gp, None, [2] * (channels // 2))
+
+
+def test_backward_reusing_the_forward_workspace(cuda_lib, oracle):
+    # workspace_holds_setup = 1: setup records and tile coverage flags of the forward call are reused
+    import torch
+    from dirt_b200 import rasterise_ops as ops
+    s = scenes.config3(batch=3, width=160, height=96, level=2, background='uniform')
+    t = _cuda(s)
+    pixels, ids, ws = ops.rasterise_forward_raw(t['background'], t['vertices'], t['vertex_colors'], t['faces'], True, True)
+    gp = torch.from_numpy(np.random.default_rng(5).standard_normal(tuple(pixels.shape)).astype(np.float32)).cuda()
+    reused = ops.rasterise_backward_raw(t['vertices'], t['faces'], pixels, gp, ids, None, ws)
+    fresh = ops.rasterise_backward_raw(t['vertices'], t['faces'], pixels, gp, ids, None, None)
+    gb_o, gv_o, gc_o = oracle.backward(s['vertices'], s['faces'], pixels.cpu().numpy(), gp.cpu().numpy())
+    for got in (reused, fresh):
+        np.testing.assert_array_equal(got[0].cpu().numpy(), gb_o)
+        assert rel_close(got[1].cpu().numpy(), gv_o)[0] and rel_close(got[2].cpu().numpy(), gc_o)[0]
+
+
+def test_kernel_timer_hooks(cuda_lib):
+    import torch
+    from dirt_b200 import rasterise_ops as ops
+    s = scenes.config3(batch=1, width=64, height=64, level=1)
+    t = _cuda(s)
+    assert cuda_lib.dirt_kernel_timer_enable(1) == 0
+    ops.rasterise_forward_raw(t['background'], t['vertices'], t['vertex_colors'], t['faces'])
+    ms = float(cuda_lib.dirt_kernel_timer_elapsed_ms())
+    assert 0.0 < ms < 1000.0
+    assert cuda_lib.dirt_kernel_timer_enable(0) == 0
+    assert cuda_lib.dirt_kernel_timer_enable(7) != 0
+    assert cuda_lib.dirt_last_launch_count() >= 0
+
+
+def test_full_size_properties(cuda_lib):
+    # BASELINE cfg3 at its full frame size (reduced batch): size-independent properties of the CUDA path
+    import torch
+    from dirt_b200 import rasterise_ops as ops
+    s = scenes.config3(batch=4, width=512, height=512, background='uniform')
+    t = _cuda(s)
+    pixels, ids = ops.rasterise_forward_raw(t['background'], t['vertices'], t['vertex_colors'], t['faces'])
+    cov = ids >= 0
+    assert 0.40 < float(cov.float().mean()) < 0.48
+    # uncovered pixels are the background, bit for bit; covered pixels of the mask channel are exactly 1 (all vertices have 1)
+    assert torch.equal(pixels[~cov], t['background'][~cov])
+    assert torch.equal(pixels[..., 0][cov], torch.ones_like(pixels[..., 0][cov]))
+    # the normal channels of a unit sphere stay unit length up to interpolation across small faces
+    n = pixels[..., 1:][cov].norm(dim=-1)
+    assert float(n.min()) > 0.99 and float(n.max()) < 1.0 + 1e-5
+    # linearity of the backward pass in grad_pixels; grad_background + coverage partition grad_pixels
+    g1 = torch.randn_like(pixels); g2 = torch.randn_like(pixels)
+    b1 = ops.rasterise_backward_raw(t['vertices'], t['faces'], pixels, g1, ids)
+    b2 = ops.rasterise_backward_raw(t['vertices'], t['faces'], pixels, g2, ids)
+    b12 = ops.rasterise_backward_raw(t['vertices'], t['faces'], pixels, g1 + 2 * g2, ids)
+    for k in (1, 2):
+        ref = b1[k] + 2 * b2[k]
+        assert float((b12[k] - ref).abs().max()) <= 2e-4 * float(ref.abs().max())
+    assert torch.equal(b1[0][~cov], g1[~cov]) and float(b1[0][cov].abs().max()) == 0.0
+    assert float(b1[1][..., 2].abs().max()) == 0.0

@@ -182,3 +182,38 @@ def test_behind_camera_faces_use_homogeneous_path(oracle):
     assert np.isfinite(gbuf[0][cov]).all()
     assert (gbuf[0][..., 3][cov] > 0).all()
     np.testing.assert_allclose(gbuf[0][..., :3][cov].sum(-1), 1.0, atol=1e-5)
+
+
+def test_random_planar_triangulations_are_covered_exactly_once(oracle):
+    # property test (hypothesis): a Delaunay-like fan triangulation of random points in the plane z=0, w=1 has
+    # no overlaps, so every pixel is claimed by at most one face and the claimed set equals the exact rational rule
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=15, deadline=None)
+    @given(st.integers(0, 10 ** 6))
+    def check(seed):
+        rng = np.random.default_rng(seed)
+        n = int(rng.integers(5, 9))
+        angles = np.sort(rng.uniform(0, 2 * np.pi, n))
+        radius = rng.uniform(0.3, 0.9, n)
+        centre = rng.uniform(-0.1, 0.1, 2)
+        ring = centre + np.stack([np.cos(angles), np.sin(angles)], 1) * radius[:, None]
+        verts = np.concatenate([np.concatenate([[centre], ring]), np.zeros((n + 1, 1)), np.ones((n + 1, 1))], axis=1).astype(np.float32)
+        faces = np.array([[0, 1 + i, 1 + (i + 1) % n] for i in range(n)], np.int32)
+        # keep only fans whose consecutive angles are < pi apart (star-shaped, non-overlapping)
+        gaps = np.diff(np.concatenate([angles, [angles[0] + 2 * np.pi]]))
+        if gaps.max() >= np.pi * 0.95:
+            return
+        H, W = 24, 28
+        ids, gbuf = oracle.visibility(verts[None], faces[None], H, W)
+        masks = numpy_oracle.coverage_exact(verts, faces, H, W)
+        count = np.sum(masks, axis=0)
+        assert count.max() <= 1
+        for f, m in enumerate(masks):
+            np.testing.assert_array_equal(ids[0] == f, m)
+        cov = ids[0] >= 0
+        if cov.any():
+            np.testing.assert_allclose(gbuf[0][..., :3][cov].sum(-1), 1.0, atol=1e-5)
+            np.testing.assert_allclose(gbuf[0][..., 3][cov], 1.0, rtol=1e-6)
+
+    check()
