@@ -320,7 +320,7 @@ def run_ours(args):
     # end to end with host buffers
     e2e = None
     if not args.no_e2e:
-        host = HostStep(prep)
+        host = HostStep(prep, chunks=args.e2e_chunks)
         for _ in range(2):
             host.step()
         sync_all()
@@ -464,6 +464,7 @@ def main():
     ap.add_argument('--batch', type=int, default=0, help='override the per-GPU batch (debugging)')
     ap.add_argument('--cpu-sample', type=int, default=64, help='images the CPU baseline renders per pass')
     ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--e2e-chunks', type=int, default=8, help='batch chunks of the host copy/compute pipeline')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     args = ap.parse_args()
     if args.impl == 'reference':

@@ -22,7 +22,7 @@ class HostRasteriser:
     of the shapes given at construction.  Results are valid after the returned event / `synchronize()`.
     """
 
-    def __init__(self, B, H, W, C, V, F, device=None, chunks=4):
+    def __init__(self, B, H, W, C, V, F, device=None, chunks=8):
         self.lib = _lib.lib()
         self.device = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
         self.shape = (B, H, W, C, V, F)
