@@ -124,10 +124,11 @@ __device__ inline bool planes_double(const float p[3][4], int H, int W, double g
     const double c22 = dsub(__dmul_rn(x0, y1), __dmul_rn(x1, y0));
     const double det = __dadd_rn(__dadd_rn(__dmul_rn(x0, c00), __dmul_rn(y0, c10)), __dmul_rn(w0, c20));
     if (!(det != 0.0) || !isfinite(det)) return false;
+    const double rdet = __ddiv_rn(1.0, det);   // one division, then products (as the specification says)
     double inv[3][3];
-    inv[0][0] = __ddiv_rn(c00, det); inv[0][1] = __ddiv_rn(c01, det); inv[0][2] = __ddiv_rn(c02, det);
-    inv[1][0] = __ddiv_rn(c10, det); inv[1][1] = __ddiv_rn(c11, det); inv[1][2] = __ddiv_rn(c12, det);
-    inv[2][0] = __ddiv_rn(c20, det); inv[2][1] = __ddiv_rn(c21, det); inv[2][2] = __ddiv_rn(c22, det);
+    inv[0][0] = __dmul_rn(c00, rdet); inv[0][1] = __dmul_rn(c01, rdet); inv[0][2] = __dmul_rn(c02, rdet);
+    inv[1][0] = __dmul_rn(c10, rdet); inv[1][1] = __dmul_rn(c11, rdet); inv[1][2] = __dmul_rn(c12, rdet);
+    inv[2][0] = __dmul_rn(c20, rdet); inv[2][1] = __dmul_rn(c21, rdet); inv[2][2] = __dmul_rn(c22, rdet);
     const double two_over_W = __ddiv_rn(2.0, (double)W), two_over_H = __ddiv_rn(2.0, (double)H);
     const double inv_W = __ddiv_rn(1.0, (double)W), inv_H = __ddiv_rn(1.0, (double)H);
 #pragma unroll

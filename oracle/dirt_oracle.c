@@ -48,7 +48,8 @@
  *      With pixel centres at (256c+128, 256r+128):
  *         q = floor((128*(A+B) + C - (topleft ? 0 : 1)) / 256)
  *         pixel (r,c) is covered  <=>  for all k: A_k*c + B_k*r + q_k >= 0     (int64)
- *  S6  interpolation planes come from the inverse of M = [x_k y_k w_k] (rows k) in double:
+ *  S6  interpolation planes come from the inverse of M = [x_k y_k w_k] (rows k) in double
+ *      (inverse = cofactors * (1/det): one division, nine products):
  *      for a target t_k, (a,b,c) = M^-1 t solves a*x_k + b*y_k + c*w_k = t_k, and
  *      f(px,py) = a*px + b*py + c is the screen-space-affine function with f(ndc_k) = t_k/w_k.
  *      Converted to pixel indices (col,row):  gA = a*(2/W), gB = -b*(2/H),
@@ -171,9 +172,10 @@ static void setup_tri(const float* verts, const int32_t* face, int V, int H, int
     double c20 = x1 * y2 - x2 * y1, c21 = x2 * y0 - x0 * y2, c22 = x0 * y1 - x1 * y0;
     double det = (x0 * c00 + y0 * c10) + w0 * c20;
     if (!(det != 0.0) || !isfinite(det)) return;
-    double inv[3][3] = {{c00 / det, c01 / det, c02 / det},
-                        {c10 / det, c11 / det, c12 / det},
-                        {c20 / det, c21 / det, c22 / det}};
+    const double rdet = 1.0 / det; /* one division, then products: part of the specification (S6) */
+    double inv[3][3] = {{c00 * rdet, c01 * rdet, c02 * rdet},
+                        {c10 * rdet, c11 * rdet, c12 * rdet},
+                        {c20 * rdet, c21 * rdet, c22 * rdet}};
     const double two_over_W = 2.0 / (double)W, two_over_H = 2.0 / (double)H;
     const double inv_W = 1.0 / (double)W, inv_H = 1.0 / (double)H;
     double gq[3][3], gs[3], gz[3];
