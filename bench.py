@@ -201,8 +201,9 @@ def cpu_baseline(scene, grad_pixels, sample_images, threads=None, min_seconds=10
             threads = len(os.sched_getaffinity(0))
         except AttributeError:
             threads = os.cpu_count() or 1
-    oracle.set_threads(threads)
     n = min(sample_images, scene['background'].shape[0])
+    threads = max(1, min(threads, n))   # the oracle parallelises over images: idle OpenMP threads only steal SMT siblings
+    oracle.set_threads(threads)
     sub = {k: np.ascontiguousarray(v[:n]) for k, v in scene.items()}
     gp = np.ascontiguousarray(grad_pixels[:n])
 
@@ -410,12 +411,13 @@ def run_reference(args):
     oracle.build()
     # all the host threads this process may use (torchrun exports OMP_NUM_THREADS=1 for its workers)
     try:
-        oracle.set_threads(len(os.sched_getaffinity(0)))
+        host_threads = len(os.sched_getaffinity(0))
     except AttributeError:
-        oracle.set_threads(os.cpu_count() or 1)
+        host_threads = os.cpu_count() or 1
     gen, kwargs, desc = WORKLOADS[args.workload]
     kwargs = dict(kwargs)
     sample = min(args.cpu_sample, kwargs.get('batch', 1))
+    oracle.set_threads(max(1, min(host_threads, sample)))   # one image per thread is the port's parallel grain
     kwargs['batch'] = sample if 'batch' in kwargs else None
     if kwargs.get('batch') is None:
         kwargs.pop('batch', None)
