@@ -138,6 +138,7 @@ class PreparedStep:
         self.ws_bytes = int(self.lib.dirt_workspace_bytes(B, H, W, C, V, F))
         self.workspace = torch.empty(self.ws_bytes, dtype=torch.uint8, device=device)
         self.launches_per_step = 0
+        self.graph = None
 
     def _p(self, t):
         return ctypes.c_void_p(t.data_ptr())
@@ -161,13 +162,37 @@ class PreparedStep:
         self._check(rc, 'RasteriseGrad')
         return self.lib.dirt_last_launch_count()
 
-    def step(self, world):
+    def local_step(self):
+        """forward + backward + the shard-local reduction of the shared-geometry gradient (no collective)."""
         n = self.forward()
         n += self.backward()
-        # shared-geometry reduction: sum the per-item vertex gradients of this shard, all-reduce across GPUs
-        from dirt_b200.distributed import reduce_shared_vertex_grads
-        reduce_shared_vertex_grads(self.grad_vertices, self.grad_vertex_colors, out=self.shared_grad)
+        self.torch.sum(self.grad_vertices, dim=0, out=self.shared_grad[:, :4])
+        self.torch.sum(self.grad_vertex_colors, dim=0, out=self.shared_grad[:, 4:])
         self.launches_per_step = n
+        return n
+
+    def capture(self):
+        """Record local_step() into a CUDA graph (every C-ABI call only enqueues work on the given stream)."""
+        torch = self.torch
+        side = torch.cuda.Stream(self.device)
+        side.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(side):
+            self.local_step()
+        torch.cuda.current_stream(self.device).wait_stream(side)
+        torch.cuda.synchronize(self.device)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.local_step()
+
+    def step(self, world):
+        if self.graph is not None:
+            self.graph.replay()
+            n = self.launches_per_step
+        else:
+            n = self.local_step()
+        if world > 1:   # the one exchange of the path: all-reduce of the [V, 4+C] shared-geometry gradient
+            import torch.distributed as dist
+            dist.all_reduce(self.shared_grad, op=dist.ReduceOp.SUM)
         return n
 
 
@@ -259,6 +284,9 @@ def run_ours(args):
             dist.barrier()
             torch.cuda.synchronize(device)
 
+    prep.local_step()
+    if not args.no_graph:
+        prep.capture()
     for _ in range(max(args.warmup, 3)):
         prep.step(world)
     sync_all()
@@ -385,7 +413,7 @@ def run_ours(args):
                    'collective': 'all_reduce(sum over batch of grad_vertices|grad_vertex_colors, [V,%d] fp32)' % (4 + C) if world > 1 else 'none (N=1)',
                    'l2': 'inputs larger than L2 (%.0f MB touched per step)' % ((fwd_bytes + bwd_bytes) / 1e6)},
         'phases_ms': {'forward_call': fwd_ms, 'backward_call': bwd_ms},
-        'gpu_launches': int(launches), 'gpu_launches_per_step': int(prep.launches_per_step),
+        'gpu_launches': int(launches), 'gpu_launches_per_step': int(prep.launches_per_step), 'cuda_graph': prep.graph is not None,
         'clocks': clocks, 'roofline': roofline,
     }
     if e2e:
@@ -466,6 +494,7 @@ def main():
     ap.add_argument('--batch', type=int, default=0, help='override the per-GPU batch (debugging)')
     ap.add_argument('--cpu-sample', type=int, default=64, help='images the CPU baseline renders per pass')
     ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--no-graph', action='store_true', help='launch every step call by call instead of replaying a CUDA graph')
     ap.add_argument('--e2e-chunks', type=int, default=8, help='batch chunks of the host copy/compute pipeline')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     args = ap.parse_args()

@@ -62,6 +62,7 @@ struct Workspace {
     int* pool_cursor;     // [1] (+ padding)
     int* refs;            // [SMALL_TILE_LIMIT*B*F]
     int32_t* face_ids;    // [B*H*W] (used when the caller does not supply a buffer)
+    size_t zero_bytes;    // bytes from tile_count that the forward pass zeroes (counts, flags, large counts, cursor)
     size_t bytes;
 };
 
@@ -78,12 +79,14 @@ inline Workspace carve_workspace(void* base, int B, int H, int W, int F)
     ws.cov = (TriCov*)take(BF * sizeof(TriCov));
     ws.itp = (TriInterp*)take(BF * sizeof(TriInterp));
     ws.tri_bin = (uint2*)take(BF * sizeof(uint2));
+    // the four blocks the forward pass must zero are adjacent: one memset covers [tile_count, zero_end)
     ws.tile_count = (int*)take(BT * sizeof(int));
     ws.tile_flags = (unsigned char*)take(BT);
-    ws.tile_range = (int2*)take(BT * sizeof(int2));
     ws.large_count = (int*)take((size_t)B * sizeof(int));
-    ws.large_list = (int*)take(BF * sizeof(int));
     ws.pool_cursor = (int*)take(256);
+    ws.zero_bytes = (size_t)((p + off) - (char*)ws.tile_count);
+    ws.tile_range = (int2*)take(BT * sizeof(int2));
+    ws.large_list = (int*)take(BF * sizeof(int));
     ws.refs = (int*)take(BF * SMALL_TILE_LIMIT * sizeof(int));
     ws.face_ids = (int32_t*)take((size_t)B * H * W * sizeof(int32_t));
     ws.bytes = off;

@@ -254,10 +254,7 @@ cudaError_t launch_setup_and_bin(const float* vertices, const int32_t* faces, co
     const long long total = (long long)d.B * d.F;
     const long long total_tiles = (long long)d.B * d.tiles;
     cudaError_t e;
-    if ((e = cudaMemsetAsync(ws.tile_count, 0, sizeof(int) * (size_t)total_tiles, stream)) != cudaSuccess) return e;
-    if ((e = cudaMemsetAsync(ws.tile_flags, 0, (size_t)total_tiles, stream)) != cudaSuccess) return e;
-    if ((e = cudaMemsetAsync(ws.large_count, 0, sizeof(int) * (size_t)d.B, stream)) != cudaSuccess) return e;
-    if ((e = cudaMemsetAsync(ws.pool_cursor, 0, 256, stream)) != cudaSuccess) return e;
+    if ((e = cudaMemsetAsync(ws.tile_count, 0, ws.zero_bytes, stream)) != cudaSuccess) return e;
     if (total > 0) {
         setup_kernel<true><<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(vertices, faces, ws, d);
         ++*launches;
