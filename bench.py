@@ -275,6 +275,8 @@ def run_ours(args):
     if 'seed' not in kwargs and args.workload != 'cfg2':
         kwargs['seed'] = 1 + rank  # every rank renders different poses
     scene = getattr(scenes, gen)(**kwargs)
+    if args.background == 'uniform':   # BASELINE's workloads use a zero background; this variant rules out any zero-data effect
+        scene['background'] = np.random.default_rng(100 + rank).uniform(size=scene['background'].shape).astype(np.float32)
     prep = PreparedStep(scene, device)
     B, H, W, C, V, F = prep.dims
 
@@ -411,6 +413,7 @@ def run_ours(args):
         'config': {'workload': desc, 'name': args.workload, 'batch_per_gpu': B, 'global_batch': B * world, 'height': H, 'width': W,
                    'channels': C, 'vertices': V, 'faces': F, 'parallelism': 'batch-sharded x%d' % world,
                    'collective': 'all_reduce(sum over batch of grad_vertices|grad_vertex_colors, [V,%d] fp32)' % (4 + C) if world > 1 else 'none (N=1)',
+                   'background': args.background,
                    'l2': 'inputs larger than L2 (%.0f MB touched per step)' % ((fwd_bytes + bwd_bytes) / 1e6)},
         'phases_ms': {'forward_call': fwd_ms, 'backward_call': bwd_ms},
         'gpu_launches': int(launches), 'gpu_launches_per_step': int(prep.launches_per_step), 'cuda_graph': prep.graph is not None,
@@ -493,6 +496,7 @@ def main():
     ap.add_argument('--workload', default='cfg3', choices=sorted(WORKLOADS))
     ap.add_argument('--batch', type=int, default=0, help='override the per-GPU batch (debugging)')
     ap.add_argument('--cpu-sample', type=int, default=64, help='images the CPU baseline renders per pass')
+    ap.add_argument('--background', default='zeros', choices=['zeros', 'uniform'], help='background values (BASELINE: zeros)')
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-graph', action='store_true', help='launch every step call by call instead of replaying a CUDA graph')
     ap.add_argument('--e2e-chunks', type=int, default=8, help='batch chunks of the host copy/compute pipeline')
