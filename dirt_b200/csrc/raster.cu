@@ -97,9 +97,7 @@ __device__ __forceinline__ void consume_list(const int* __restrict__ list, int c
                                              Slot* slots, int lane, int tcol0, int trow0, int H, int W, Quad& quad,
                                              uint32_t& tile_max)
 {
-    const int dx = (lane & 7) * 2, dy = (lane >> 3) * 2;
-    const int col0 = tcol0 + dx, row0 = trow0 + dy;
-    const float c0f = (float)col0, c1f = (float)(col0 + 1), r0f = (float)row0, r1f = (float)(row0 + 1);
+    int col0 = tcol0 + (lane & 7) * 2, row0 = trow0 + (lane >> 3) * 2;   // this lane's quad: (row0..row0+1) x (col0..col0+1)
     const float tc0 = (float)tcol0, tc1 = (float)(tcol0 + TILE_W - 1), tr0 = (float)trow0, tr1 = (float)(trow0 + TILE_H - 1);
 
     for (int base = 0; base < count; base += 32) {
@@ -161,22 +159,27 @@ __device__ __forceinline__ void consume_list(const int* __restrict__ list, int c
             const uint32_t nearest = __reduce_min_sync(0xffffffffu, order);
             // strict: a face whose nearest key ties the farthest covered pixel could still win on face index
             if (nearest == 0xFFFFFFFFu || (nearest >> 5) > tile_max) break;
-            const int j = nearest & 31;
-            if (lane == j) order = 0xFFFFFFFFu;
-            const Slot s = slots[j];
+            order = (order == nearest) ? 0xFFFFFFFFu : order;   // orders are unique (the lane index sits in the low bits)
+            const Slot s = slots[nearest & 31];
+            // Keep just (col0,row0) live across iterations and derive the other per-lane constants here: under the
+            // 64-register cap the compiler otherwise spills them or rebuilds them from %tid/%ctaid every iteration.
+            asm volatile("" : "+r"(col0), "+r"(row0));
+            const int dx = col0 - tcol0, dy = row0 - trow0;
+            const float c0f = (float)col0, c1f = (float)(col0 + 1), r0f = (float)row0, r1f = (float)(row0 + 1);
             uint32_t k00, k01, k10, k11;
             if (SMALL || s.kind != (int32_t)KIND_HARD) {
                 const int32_t a0 = s.Q0 + s.A0 * dx + s.B0 * dy, a1 = s.Q1 + s.A1 * dx + s.B1 * dy, a2 = s.Q2 + s.A2 * dx + s.B2 * dy;
-                const bool in00 = (a0 | a1 | a2) >= 0;
-                const bool in01 = ((a0 + s.A0) | (a1 + s.A1) | (a2 + s.A2)) >= 0;
                 const int32_t b0 = a0 + s.B0, b1 = a1 + s.B1, b2 = a2 + s.B2;
-                const bool in10 = (b0 | b1 | b2) >= 0;
-                const bool in11 = ((b0 + s.A0) | (b1 + s.A1) | (b2 + s.A2)) >= 0;
+                // all-ones where any edge function is negative (pixel outside): OR-ing it in turns the key into "no fragment"
+                const uint32_t out00 = (uint32_t)((a0 | a1 | a2) >> 31);
+                const uint32_t out01 = (uint32_t)(((a0 + s.A0) | (a1 + s.A1) | (a2 + s.A2)) >> 31);
+                const uint32_t out10 = (uint32_t)((b0 | b1 | b2) >> 31);
+                const uint32_t out11 = (uint32_t)(((b0 + s.A0) | (b1 + s.A1) | (b2 + s.A2)) >> 31);
                 const float zr0 = __fmaf_rn(s.zB, r0f, s.zC), zr1 = __fmaf_rn(s.zB, r1f, s.zC);
-                k00 = in00 ? exact::depth_key(__fmaf_rn(s.zA, c0f, zr0)) : 0xFFFFFFFFu;
-                k01 = in01 ? exact::depth_key(__fmaf_rn(s.zA, c1f, zr0)) : 0xFFFFFFFFu;
-                k10 = in10 ? exact::depth_key(__fmaf_rn(s.zA, c0f, zr1)) : 0xFFFFFFFFu;
-                k11 = in11 ? exact::depth_key(__fmaf_rn(s.zA, c1f, zr1)) : 0xFFFFFFFFu;
+                k00 = exact::depth_key(__fmaf_rn(s.zA, c0f, zr0)) | out00;
+                k01 = exact::depth_key(__fmaf_rn(s.zA, c1f, zr0)) | out01;
+                k10 = exact::depth_key(__fmaf_rn(s.zA, c0f, zr1)) | out10;
+                k11 = exact::depth_key(__fmaf_rn(s.zA, c1f, zr1)) | out11;
             } else {
                 const uint4 k = hard_face_keys(verts, itp_b, s.face, H, W, col0, row0);
                 k00 = k.x; k01 = k.y; k10 = k.z; k11 = k.w;
