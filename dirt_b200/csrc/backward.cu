@@ -209,8 +209,11 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
 struct PixelTerms {      // everything one pixel contributes (fast path)
     int key_col;         // own face (-1: uncovered)
     int key_pos;         // face receiving the position gradient (-1: none)
-    float bc0, bc1, bc2; // undilated barycentrics
-    float bp0, bp1, bp2; // barycentrics used for the position gradient
+    // barycentrics (c: undilated, for the colour terms; p: of the fragment receiving the position gradient), arranged for
+    // the first butterfly step: A = the vertex whose sums this lane keeps (vertex 0 on lanes 0-15, vertex 1 on lanes
+    // 16-31), B = the one it hands to its partner, 2 = vertex 2
+    float cA, cB, c2;
+    float pA, pB, p2;
 };
 
 struct Fragment {   // a face seen at a pixel: G-buffer entry + vertex ids
@@ -361,15 +364,16 @@ struct TransposedReduce {
         TransposedReduce<H, STEPS - 1>::run(w, lane, bit >> 1, out);
     }
     // global index of out[0] on this lane: out[i] is sum base+i (entries beyond the valid range are padding)
-    static __device__ __forceinline__ int base(int lane, int bit)
+    static __host__ __device__ constexpr int base(int lane, int bit)
     {
         return ((lane & bit) ? H : 0) + TransposedReduce<H, STEPS - 1>::base(lane, bit >> 1);
     }
     // is out[i] a real sum?  (checks the padding introduced at every level)
-    static __device__ __forceinline__ bool valid(int lane, int bit, int i)
+    static __host__ __device__ constexpr bool valid(int lane, int bit, int i)
     {
-        const int p = TransposedReduce<H, STEPS - 1>::base(lane, bit >> 1) + i;   // position inside this level's kept half
-        return TransposedReduce<H, STEPS - 1>::valid(lane, bit >> 1, i) && (((lane & bit) ? H : 0) + p < N);
+        // p: position inside this level's kept half
+        return TransposedReduce<H, STEPS - 1>::valid(lane, bit >> 1, i) &&
+               (((lane & bit) ? H : 0) + TransposedReduce<H, STEPS - 1>::base(lane, bit >> 1) + i < N);
     }
 };
 template <int N>
@@ -380,9 +384,51 @@ struct TransposedReduce<N, 0> {
 #pragma unroll
         for (int i = 0; i < N; ++i) out[i] = v[i];
     }
-    static __device__ __forceinline__ int base(int, int) { return 0; }
-    static __device__ __forceinline__ bool valid(int, int, int i) { return i < N; }
+    static __host__ __device__ constexpr int base(int, int) { return 0; }
+    static __host__ __device__ constexpr bool valid(int, int, int i) { return i < N; }
 };
+
+// Which finished sum a lane owns after the butterfly, as a destination: bits 0-1 = vertex k of the face, bits 2-3 =
+// component inside the vertex's row, bit 4 = row of grad_vertices (else grad_vertex_colors); -1 = none.  A table in
+// constant memory because the compiler, short of registers, otherwise recomputes the index arithmetic (~40 instructions)
+// for every face of every tile.
+template <int C>
+struct OwnerTable {
+    int meta[32];
+};
+template <int C>
+constexpr OwnerTable<C> make_owner_table()
+{
+    // layout after the first (operand-level) butterfly step, see the per-face reduction: NS sums of vertex 0 (lanes
+    // 0-15) or vertex 1 (lanes 16-31), then the lower / upper half of the NS sums of vertex 2
+    constexpr int NS = C + 3, H2 = (NS + 1) / 2;
+    using Red = TransposedReduce<NS + H2, 4>;
+    OwnerTable<C> t{};
+    for (int lane = 0; lane < 32; ++lane) {
+        int m = -1;
+        if (Red::valid(lane, 8, 0)) {
+            const int q = Red::base(lane, 8);
+            const bool up = (lane & 16) != 0;
+            const int k = q < NS ? (up ? 1 : 0) : 2;
+            const int j = q < NS ? q : (q - NS) + (up ? H2 : 0);
+            if (j < NS) {
+                const bool pos = j >= C;
+                const int comp = pos ? (j - C == 2 ? 3 : j - C) : j;   // a, b, c go to x, y, w of the vertex row
+                m = k | (comp << 2) | (pos ? 16 : 0);
+            }
+        }
+        t.meta[lane] = m;
+    }
+    return t;
+}
+__constant__ OwnerTable<1> c_owner1 = make_owner_table<1>();
+__constant__ OwnerTable<3> c_owner3 = make_owner_table<3>();
+__constant__ OwnerTable<4> c_owner4 = make_owner_table<4>();
+template <int C>
+__device__ __forceinline__ int owner_meta(int lane)
+{
+    return C == 1 ? c_owner1.meta[lane] : C == 3 ? c_owner3.meta[lane] : c_owner4.meta[lane];
+}
 
 template <int C>
 __global__ void __launch_bounds__(BWD_WARPS_PER_BLOCK * 32, DIRT_BWD_MIN_BLOCKS) backward_tile_kernel(
@@ -391,7 +437,6 @@ __global__ void __launch_bounds__(BWD_WARPS_PER_BLOCK * 32, DIRT_BWD_MIN_BLOCKS)
     float* __restrict__ grad_vertex_colors, Workspace ws, Dims d, const unsigned char* __restrict__ tile_flags)
 {
     constexpr int NS = C + 3;                  // scalars per pixel: C colour + (a,b,c)
-    constexpr int NV = 3 * NS;                 // sums per face
     constexpr int N0 = (C == 1) ? 1 : 3;       // width of the first group
     constexpr bool TWO_GROUPS = (C == 4);      // {3,1}
     constexpr int REACH = (C == 3) ? 1 : 3;    // columns to the right of the pixel that its taps read
@@ -526,6 +571,7 @@ __global__ void __launch_bounds__(BWD_WARPS_PER_BLOCK * 32, DIRT_BWD_MIN_BLOCKS)
     __syncwarp();
 
     // ---- per-pixel terms -------------------------------------------------------------------------------------
+    const bool upper = (lane & 16) != 0;   // which half of the warp: decides the arrangement of the weights in PixelTerms
     PixelTerms term[2];
     float sc[2][NS];    // scalars: [0,C) grad_pixels, C..C+2 = a,b,c
 #pragma unroll
@@ -533,16 +579,16 @@ __global__ void __launch_bounds__(BWD_WARPS_PER_BLOCK * 32, DIRT_BWD_MIN_BLOCKS)
         const int row = row0 + pix;
         PixelTerms& T = term[pix];
         T.key_col = T.key_pos = -1;
-        T.bc0 = T.bc1 = T.bc2 = T.bp0 = T.bp1 = T.bp2 = 0.f;
+        T.cA = T.cB = T.c2 = T.pA = T.pB = T.p2 = 0.f;
 #pragma unroll
         for (int i = 0; i < NS; ++i) sc[pix][i] = (i < C) ? gp[pix][i % C] : 0.f;
         if (f_own[pix] == -2) continue;
         const Fragment& me = own[pix];
         const bool interior = col > 0 && row > 0 && col < W - 1 && row < H - 1;
         T.key_col = me.face;
-        if (me.face >= 0) { T.bc0 = me.g.x; T.bc1 = me.g.y; T.bc2 = me.g.z; }
+        if (me.face >= 0) { T.cA = upper ? me.g.y : me.g.x; T.cB = upper ? me.g.x : me.g.y; T.c2 = me.g.z; }
 #if DIRT_ABLATE >= 2
-        T.key_pos = me.face; T.bp0 = T.bc0; T.bp1 = T.bc1; T.bp2 = T.bc2;
+        T.key_pos = me.face; T.pA = T.cA; T.pB = T.cB; T.p2 = T.c2;
         sc[pix][C] = gp[pix][0]; sc[pix][C + 1] = gp[pix][0]; sc[pix][C + 2] = gp[pix][0];
         continue;
 #endif
@@ -609,7 +655,7 @@ __global__ void __launch_bounds__(BWD_WARPS_PER_BLOCK * 32, DIRT_BWD_MIN_BLOCKS)
         }
         if (pos0.face >= 0) {
             T.key_pos = pos0.face;
-            T.bp0 = pos0.g.x; T.bp1 = pos0.g.y; T.bp2 = pos0.g.z;
+            T.pA = upper ? pos0.g.y : pos0.g.x; T.pB = upper ? pos0.g.x : pos0.g.y; T.p2 = pos0.g.z;
             position_terms(pos0, dLdx, dLdy, sc[pix][C], sc[pix][C + 1], sc[pix][C + 2]);
         }
     }
@@ -621,8 +667,7 @@ __global__ void __launch_bounds__(BWD_WARPS_PER_BLOCK * 32, DIRT_BWD_MIN_BLOCKS)
     // directly, all such faces of the tile together, in one pass of vector REDs at the end.
 #if DIRT_ABLATE != 1
     {
-        using Red = TransposedReduce<NV, 5>;
-        const int owner = Red::valid(lane, 16, 0) ? Red::base(lane, 16) : -1;
+        const int owner = owner_meta<C>(lane);
         const int kc0 = term[0].key_col, kc1 = term[1].key_col, kp0 = term[0].key_pos, kp1 = term[1].key_pos;
         unsigned direct = 0;   // bit 0/1: colour record of pixel 0/1, bit 2/3: position record of pixel 0/1
         int last = -1;
@@ -646,30 +691,43 @@ __global__ void __launch_bounds__(BWD_WARPS_PER_BLOCK * 32, DIRT_BWD_MIN_BLOCKS)
                 continue;
             }
 #endif
-            float v[NV];
+            // First butterfly step at operand level: this lane keeps the NS sums of vertex A and hands those of vertex B
+            // to lane^16 (the weights were arranged per half-warp when they were stored), and the halves swap one half
+            // each of the NS sums of vertex 2.  The remaining steps are the generic transposed butterfly.
+            constexpr int H2 = (NS + 1) / 2;
+            float keep[NS], send[NS], third[NS];
 #pragma unroll
             for (int pix = 0; pix < 2; ++pix) {
                 const PixelTerms& T = term[pix];
                 const bool mc = pix ? mc1 : mc0, mp = pix ? mp1 : mp0;
-                const float wc[3] = {mc ? T.bc0 : 0.f, mc ? T.bc1 : 0.f, mc ? T.bc2 : 0.f};
-                const float wp[3] = {mp ? T.bp0 : 0.f, mp ? T.bp1 : 0.f, mp ? T.bp2 : 0.f};
+                const float wcA = mc ? T.cA : 0.f, wcB = mc ? T.cB : 0.f, wc2 = mc ? T.c2 : 0.f;
+                const float wpA = mp ? T.pA : 0.f, wpB = mp ? T.pB : 0.f, wp2 = mp ? T.p2 : 0.f;
 #pragma unroll
-                for (int k = 0; k < 3; ++k) {
-#pragma unroll
-                    for (int j = 0; j < NS; ++j) {
-                        const float w = (j < C) ? wc[k] : wp[k];
-                        v[k * NS + j] = (pix == 0) ? w * sc[pix][j] : fmaf(w, sc[pix][j], v[k * NS + j]);
-                    }
+                for (int j = 0; j < NS; ++j) {
+                    const float a = (j < C) ? wcA : wpA, bb = (j < C) ? wcB : wpB, cc = (j < C) ? wc2 : wp2;
+                    keep[j] = (pix == 0) ? a * sc[pix][j] : fmaf(a, sc[pix][j], keep[j]);
+                    send[j] = (pix == 0) ? bb * sc[pix][j] : fmaf(bb, sc[pix][j], send[j]);
+                    third[j] = (pix == 0) ? cc * sc[pix][j] : fmaf(cc, sc[pix][j], third[j]);
                 }
             }
+            float v[NS + H2];
+#pragma unroll
+            for (int j = 0; j < NS; ++j) v[j] = keep[j] + __shfl_xor_sync(0xffffffffu, send[j], 16);
+#pragma unroll
+            for (int i = 0; i < H2; ++i) {
+                const float hi = (H2 + i < NS) ? third[H2 + i] : 0.f;
+                const float snd = upper ? third[i] : hi, kp = upper ? hi : third[i];
+                v[NS + i] = kp + __shfl_xor_sync(0xffffffffu, snd, 16);
+            }
             float total[1];
-            Red::run(v, lane, 16, total);
+            TransposedReduce<NS + H2, 4>::run(v, lane, 8, total);
             if (owner >= 0) {
-                const int k = owner / NS, j = owner - k * NS;
                 const int4 q = __ldg(reinterpret_cast<const int4*>(itp_b + f) + 2);   // {sC, v0, v1, v2}
+                const int k = owner & 3;
                 const int vid = (k == 0) ? q.y : (k == 1) ? q.z : q.w;
-                float* dst = (j < C) ? (gcols + (size_t)vid * C + j) : (gverts + (size_t)vid * 4 + (j - C == 2 ? 3 : j - C));
-                atomicAdd(dst, total[0]);
+                const bool pos = (owner & 16) != 0;
+                float* row = pos ? gverts : gcols;
+                atomicAdd(row + (size_t)vid * (pos ? 4 : C) + ((owner >> 2) & 3), total[0]);
             }
         }
 #if DIRT_BWD_SMALL_FACE > 0
@@ -683,7 +741,8 @@ __global__ void __launch_bounds__(BWD_WARPS_PER_BLOCK * 32, DIRT_BWD_MIN_BLOCKS)
                 const int f = colour ? T.key_col : T.key_pos;
                 const int4 q = __ldg(reinterpret_cast<const int4*>(itp_b + f) + 2);
                 const int vid[3] = {q.y, q.z, q.w};
-                const float w[3] = {colour ? T.bc0 : T.bp0, colour ? T.bc1 : T.bp1, colour ? T.bc2 : T.bp2};
+                const float wA = colour ? T.cA : T.pA, wB = colour ? T.cB : T.pB;
+                const float w[3] = {upper ? wB : wA, upper ? wA : wB, colour ? T.c2 : T.p2};
 #pragma unroll
                 for (int k = 0; k < 3; ++k) {
                     if (colour) {
