@@ -20,6 +20,9 @@ constexpr int BWD_WARPS_PER_BLOCK = DIRT_BWD_WARPS;
 #ifndef DIRT_BWD_SMALL_FACE
 #define DIRT_BWD_SMALL_FACE 12  // faces owning at most this many records in a tile are added directly (0: always reduce); profiles/r01_sweep_small_face.txt
 #endif
+#ifndef DIRT_BWD_SMALL_LANES
+#define DIRT_BWD_SMALL_LANES 0  // > 0: the criterion is the number of lanes holding a record of the face instead
+#endif
 #ifndef DIRT_BWD_MIN_BLOCKS
 #define DIRT_BWD_MIN_BLOCKS 8   // <= 64 registers: measured best (profiles/r01_sweep_bounds.txt)
 #endif
@@ -668,6 +671,9 @@ __global__ void __launch_bounds__(BWD_WARPS_PER_BLOCK * 32, DIRT_BWD_MIN_BLOCKS)
 #if DIRT_ABLATE != 1
     {
         const int owner = owner_meta<C>(lane);
+        // destination of this lane's finished sum: component (owner >> 2) & 3 of row `vid` of grad_vertices / grad_vertex_colors
+        float* const owner_row = ((owner & 16) ? gverts : gcols) + ((owner >> 2) & 3);
+        const int owner_stride = (owner & 16) ? 4 : C;
         const int kc0 = term[0].key_col, kc1 = term[1].key_col, kp0 = term[0].key_pos, kp1 = term[1].key_pos;
         unsigned direct = 0;   // bit 0/1: colour record of pixel 0/1, bit 2/3: position record of pixel 0/1
         int last = -1;
@@ -684,9 +690,15 @@ __global__ void __launch_bounds__(BWD_WARPS_PER_BLOCK * 32, DIRT_BWD_MIN_BLOCKS)
             last = f;
             const bool mc0 = kc0 == f, mc1 = kc1 == f, mp0 = kp0 == f, mp1 = kp1 == f;
 #if DIRT_BWD_SMALL_FACE > 0
+#if DIRT_BWD_SMALL_LANES > 0
+            // lanes holding a record of this face (each holds up to four): one vote instead of four
+            const int records = __popc(__ballot_sync(0xffffffffu, mc0 | mc1 | mp0 | mp1));
+            if (records <= DIRT_BWD_SMALL_LANES) {
+#else
             const int records = __popc(__ballot_sync(0xffffffffu, mc0)) + __popc(__ballot_sync(0xffffffffu, mc1)) +
                                 __popc(__ballot_sync(0xffffffffu, mp0)) + __popc(__ballot_sync(0xffffffffu, mp1));
             if (records <= DIRT_BWD_SMALL_FACE) {
+#endif
                 direct |= (mc0 ? 1u : 0u) | (mc1 ? 2u : 0u) | (mp0 ? 4u : 0u) | (mp1 ? 8u : 0u);
                 continue;
             }
@@ -723,11 +735,8 @@ __global__ void __launch_bounds__(BWD_WARPS_PER_BLOCK * 32, DIRT_BWD_MIN_BLOCKS)
             TransposedReduce<NS + H2, 4>::run(v, lane, 8, total);
             if (owner >= 0) {
                 const int4 q = __ldg(reinterpret_cast<const int4*>(itp_b + f) + 2);   // {sC, v0, v1, v2}
-                const int k = owner & 3;
-                const int vid = (k == 0) ? q.y : (k == 1) ? q.z : q.w;
-                const bool pos = (owner & 16) != 0;
-                float* row = pos ? gverts : gcols;
-                atomicAdd(row + (size_t)vid * (pos ? 4 : C) + ((owner >> 2) & 3), total[0]);
+                const int vid = (owner & 1) ? q.z : ((owner & 2) ? q.w : q.y);
+                atomicAdd(owner_row + (size_t)vid * owner_stride, total[0]);
             }
         }
 #if DIRT_BWD_SMALL_FACE > 0
