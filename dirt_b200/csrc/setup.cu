@@ -17,8 +17,15 @@ namespace dirt {
 
 constexpr float GUARD_BAND = 8388608.0f;  // 2^23 sub-pixel units = 32768 px
 
+// 128 threads x 8 blocks per SM (<= 64 registers): measured best, profiles/r01_sweep_setup.txt
+#ifndef DIRT_SETUP_THREADS
+#define DIRT_SETUP_THREADS 128
+#endif
+#ifndef DIRT_SETUP_MIN_BLOCKS
+#define DIRT_SETUP_MIN_BLOCKS 8
+#endif
 template <bool BIN>
-__global__ void __launch_bounds__(256) setup_kernel(const float* __restrict__ vertices,
+__global__ void __launch_bounds__(DIRT_SETUP_THREADS, DIRT_SETUP_MIN_BLOCKS) setup_kernel(const float* __restrict__ vertices,
                                                     const int32_t* __restrict__ faces, Workspace ws, Dims d)
 {
     const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -256,7 +263,7 @@ cudaError_t launch_setup_and_bin(const float* vertices, const int32_t* faces, co
     cudaError_t e;
     if ((e = cudaMemsetAsync(ws.tile_count, 0, ws.zero_bytes, stream)) != cudaSuccess) return e;
     if (total > 0) {
-        setup_kernel<true><<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(vertices, faces, ws, d);
+        setup_kernel<true><<<(unsigned)((total + DIRT_SETUP_THREADS - 1) / DIRT_SETUP_THREADS), DIRT_SETUP_THREADS, 0, stream>>>(vertices, faces, ws, d);
         ++*launches;
     }
     if (total_tiles > 0) {
@@ -275,7 +282,7 @@ cudaError_t launch_setup_only(const float* vertices, const int32_t* faces, const
 {
     const long long total = (long long)d.B * d.F;
     if (total > 0) {
-        setup_kernel<false><<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(vertices, faces, ws, d);
+        setup_kernel<false><<<(unsigned)((total + DIRT_SETUP_THREADS - 1) / DIRT_SETUP_THREADS), DIRT_SETUP_THREADS, 0, stream>>>(vertices, faces, ws, d);
         ++*launches;
     }
     return cudaGetLastError();
