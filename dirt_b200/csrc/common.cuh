@@ -93,6 +93,11 @@ inline Workspace carve_workspace(void* base, int B, int H, int W, int F)
     return ws;
 }
 
+// S6 constants of the NDC -> pixel-index map, divided once on the host (IEEE double, same values as on the device)
+struct PixelScale {
+    double two_over_W, two_over_H, inv_W, inv_H;
+};
+
 // ---- exactly specified arithmetic --------------------------------------------------------------
 namespace exact {
 
@@ -111,7 +116,7 @@ __device__ __forceinline__ void ndc_to_pixel_plane(double a, double b, double c,
 
 // S6: planes of q_k = beta_k/w_k (k=0..2), S = 1/clip_w and window depth, in double, absolute pixel
 // indices.  p[k] = (x,y,z,w) of vertex k.  Returns false when the face is degenerate.
-__device__ inline bool planes_double(const float p[3][4], int H, int W, double gq[3][3], double gs[3], double gz[3])
+__device__ inline bool planes_double(const float p[3][4], const PixelScale& ps, double gq[3][3], double gs[3], double gz[3])
 {
     const double x0 = p[0][0], y0 = p[0][1], w0 = p[0][3];
     const double x1 = p[1][0], y1 = p[1][1], w1 = p[1][3];
@@ -132,8 +137,7 @@ __device__ inline bool planes_double(const float p[3][4], int H, int W, double g
     inv[0][0] = __dmul_rn(c00, rdet); inv[0][1] = __dmul_rn(c01, rdet); inv[0][2] = __dmul_rn(c02, rdet);
     inv[1][0] = __dmul_rn(c10, rdet); inv[1][1] = __dmul_rn(c11, rdet); inv[1][2] = __dmul_rn(c12, rdet);
     inv[2][0] = __dmul_rn(c20, rdet); inv[2][1] = __dmul_rn(c21, rdet); inv[2][2] = __dmul_rn(c22, rdet);
-    const double two_over_W = __ddiv_rn(2.0, (double)W), two_over_H = __ddiv_rn(2.0, (double)H);
-    const double inv_W = __ddiv_rn(1.0, (double)W), inv_H = __ddiv_rn(1.0, (double)H);
+    const double two_over_W = ps.two_over_W, two_over_H = ps.two_over_H, inv_W = ps.inv_W, inv_H = ps.inv_H;
 #pragma unroll
     for (int k = 0; k < 3; ++k)
         ndc_to_pixel_plane(inv[0][k], inv[1][k], inv[2][k], two_over_W, two_over_H, inv_W, inv_H, gq[k]);
@@ -224,6 +228,7 @@ __device__ __forceinline__ TriCov load_cov(const TriCov* p)
 // ---- launch parameter blocks -------------------------------------------------------------------
 struct Dims {
     int B, H, W, C, V, F;
+    PixelScale ps;
     int tiles_x, tiles_y, tiles;     // per image, forward/binning tiles (TILE_W x TILE_H)
     int btiles_x, btiles_y, btiles;  // per image, backward tiles (8 x 8)
 };
@@ -238,6 +243,8 @@ inline Dims make_dims(int B, int H, int W, int C, int V, int F)
     d.btiles_x = (W + 7) / 8;
     d.btiles_y = (H + 7) / 8;
     d.btiles = d.btiles_x * d.btiles_y;
+    d.ps.two_over_W = 2.0 / (double)W; d.ps.two_over_H = 2.0 / (double)H;
+    d.ps.inv_W = 1.0 / (double)W; d.ps.inv_H = 1.0 / (double)H;
     return d;
 }
 

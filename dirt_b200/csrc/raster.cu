@@ -68,7 +68,12 @@ __device__ __noinline__ uint4 hard_face_keys(const float* __restrict__ verts, co
     }
     double gq[3][3], gs[3], gz[3];
     uint32_t keys[4] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu};
-    if (exact::planes_double(p, H, W, gq, gs, gz)) {
+    // the same IEEE divisions the host does for Dims::ps (kept local: this path is rare and the hot loop's register
+    // allocation is sensitive to the signature of its caller)
+    PixelScale ps;
+    ps.two_over_W = __ddiv_rn(2.0, (double)W); ps.two_over_H = __ddiv_rn(2.0, (double)H);
+    ps.inv_W = __ddiv_rn(1.0, (double)W); ps.inv_H = __ddiv_rn(1.0, (double)H);
+    if (exact::planes_double(p, ps, gq, gs, gz)) {
 #pragma unroll
         for (int pix = 0; pix < 4; ++pix) {
             const int row = row0 + (pix >> 1), col = col0 + (pix & 1);

@@ -35,169 +35,152 @@ __global__ void __launch_bounds__(DIRT_SETUP_THREADS, DIRT_SETUP_MIN_BLOCKS) set
     const int f = (int)(gid - (long long)b * d.F);
     const float* verts = vertices + (size_t)b * d.V * 4;
 
-    TriCov cov;
-    TriInterp itp;
-    cov.A0 = cov.B0 = cov.A1 = cov.B1 = cov.A2 = cov.B2 = 0;
-    cov.l.q0 = cov.l.q1 = cov.l.q2 = -1;
-    cov.l.zA = cov.l.zB = cov.l.zC = 0.f;
-    cov.s.kind = KIND_CULLED;
-    itp.q0A = itp.q0B = itp.q0C = itp.q1A = itp.q1B = itp.q1C = itp.sA = itp.sB = 0.f;
-    itp.sC = 1.f;
-    itp.v0 = itp.v1 = itp.v2 = 0;
-    itp.cref = itp.rref = 0;
-    itp.pad0 = itp.pad1 = 0;
-    uint2 bin = make_uint2(0xFFFFFFFFu, 0xFFFFFFFFu);
+    // A face that cannot produce a fragment leaves a defined record (kind = culled, edge functions negative) and is not
+    // binned.  Every rejection below ends here, so the path of a face that survives has no merges with default values.
+    const auto cull = [&]() {
+        uint4* c = reinterpret_cast<uint4*>(ws.cov + gid);
+        c[0] = make_uint4(0u, 0u, 0u, 0u);                            // A0 B0 A1 B1
+        c[1] = make_uint4(0u, 0u, 0u, 0u);                            // A2 B2 zA zB
+        c[2] = make_uint4(~0u, ~0u, ~0u, ~0u);                        // q0 = q1 = -1
+        c[3] = make_uint4(~0u, ~0u, 0u, KIND_CULLED);                 // q2 = -1, zC, kind
+        uint4* i = reinterpret_cast<uint4*>(ws.itp + gid);
+        i[0] = make_uint4(0u, 0u, 0u, 0u);
+        i[1] = make_uint4(0u, 0u, 0u, 0u);
+        i[2] = make_uint4(__float_as_uint(1.0f), 0u, 0u, 0u);         // sC = 1, v0..v2 = 0
+        i[3] = make_uint4(0u, 0u, 0u, 0u);
+        if (BIN) ws.tri_bin[gid] = make_uint2(0xFFFFFFFFu, 0xFFFFFFFFu);
+    };
 
-    int kind = 0;
-    float p[3][4];
     int32_t vid[3];
-    bool ok = true;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) vid[k] = __ldg(&faces[(size_t)gid * 3 + k]);
+    if ((unsigned)vid[0] >= (unsigned)d.V || (unsigned)vid[1] >= (unsigned)d.V || (unsigned)vid[2] >= (unsigned)d.V) { cull(); return; }
+
+    float p[3][4];
+    bool finite = true;
+    int n_behind = 0;
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
-        vid[k] = __ldg(&faces[(size_t)gid * 3 + k]);
-        if (vid[k] < 0 || vid[k] >= d.V) ok = false;
+        const float4 v = __ldg(reinterpret_cast<const float4*>(verts) + vid[k]);
+        p[k][0] = v.x; p[k][1] = v.y; p[k][2] = v.z; p[k][3] = v.w;
+        finite = finite && isfinite(v.x) && isfinite(v.y) && isfinite(v.z) && isfinite(v.w);
+        if (!(v.w > 0.0f)) ++n_behind;
     }
-    if (ok) {
+    if (!finite || n_behind == 3) { cull(); return; }
+
+    // S1-S3: window coordinates snapped to 1/256 px; a vertex behind the eye or outside the guard band makes the face "hard"
+    bool hard = n_behind > 0;
+    int32_t xi[3] = {0, 0, 0}, yi[3] = {0, 0, 0};
+    if (!hard) {
+        const float halfW = 0.5f * (float)d.W, halfH = 0.5f * (float)d.H;
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
-            const float4 v = __ldg(reinterpret_cast<const float4*>(verts) + vid[k]);
-            p[k][0] = v.x; p[k][1] = v.y; p[k][2] = v.z; p[k][3] = v.w;
-            if (!isfinite(v.x) || !isfinite(v.y) || !isfinite(v.z) || !isfinite(v.w)) ok = false;
+            const float xn = __fdiv_rn(p[k][0], p[k][3]);
+            const float yn = __fdiv_rn(p[k][1], p[k][3]);
+            const float X = __fmul_rn(__fadd_rn(xn, 1.0f), halfW);
+            const float Y = __fmul_rn(__fsub_rn(1.0f, yn), halfH);
+            const float fx = __fmul_rn(X, 256.0f), fy = __fmul_rn(Y, 256.0f);
+            if (!(fabsf(fx) <= GUARD_BAND) || !(fabsf(fy) <= GUARD_BAND)) hard = true;
+            else { xi[k] = __float2int_rn(fx); yi[k] = __float2int_rn(fy); }
         }
     }
-    int cmin = 0, cmax = -1, rmin = 0, rmax = -1;
+
+    // S6: interpolation and depth planes
+    double gq[3][3], gs[3], gz[3];
+    if (!exact::planes_double(p, d.ps, gq, gs, gz)) { cull(); return; }
+
+    // S4-S5: edge functions and the pixel bounding box of a normal face; a hard face may touch any pixel
+    int32_t A[3] = {0, 0, 0}, Bc[3] = {0, 0, 0};
     int64_t q_abs[3] = {-1, -1, -1};
-    float zpl[3] = {0.f, 0.f, 0.f};
-    if (ok) {
-        bool hard = false;
-        int n_behind = 0;
+    int cmin = 0, cmax = d.W - 1, rmin = 0, rmax = d.H - 1;
+    if (!hard) {
+        const int64_t ax = xi[0], ay = yi[0], bx = xi[1], by = yi[1], cx = xi[2], cy = yi[2];
+        const int64_t area2 = (bx - ax) * (cy - ay) - (cx - ax) * (by - ay);
+        if (area2 == 0) { cull(); return; }
+        int32_t px[3] = {xi[0], xi[1], xi[2]}, py[3] = {yi[0], yi[1], yi[2]};
+        if (area2 < 0) {
+            int32_t t = px[1]; px[1] = px[2]; px[2] = t;
+            t = py[1]; py[1] = py[2]; py[2] = t;
+        }
 #pragma unroll
-        for (int k = 0; k < 3; ++k)
-            if (!(p[k][3] > 0.0f)) { hard = true; ++n_behind; }
-        if (n_behind == 3) ok = false;
-
-        int32_t xi[3] = {0, 0, 0}, yi[3] = {0, 0, 0};
-        if (ok && !hard) {
-            const float halfW = 0.5f * (float)d.W, halfH = 0.5f * (float)d.H;
-#pragma unroll
-            for (int k = 0; k < 3; ++k) {
-                const float xn = __fdiv_rn(p[k][0], p[k][3]);
-                const float yn = __fdiv_rn(p[k][1], p[k][3]);
-                const float X = __fmul_rn(__fadd_rn(xn, 1.0f), halfW);
-                const float Y = __fmul_rn(__fsub_rn(1.0f, yn), halfH);
-                const float fx = __fmul_rn(X, 256.0f), fy = __fmul_rn(Y, 256.0f);
-                if (!(fabsf(fx) <= GUARD_BAND) || !(fabsf(fy) <= GUARD_BAND)) hard = true;
-                else { xi[k] = __float2int_rn(fx); yi[k] = __float2int_rn(fy); }
-            }
+        for (int k = 0; k < 3; ++k) {
+            const int a = (k + 1) % 3, bb = (k + 2) % 3;
+            const int64_t Ak = (int64_t)py[a] - py[bb];
+            const int64_t Bk = (int64_t)px[bb] - px[a];
+            const int64_t Ck = -(Ak * px[a] + Bk * py[a]);
+            const bool tl = (Ak > 0) || (Ak == 0 && Bk > 0);
+            const int64_t Cpp = 128 * (Ak + Bk) + Ck - (tl ? 0 : 1);
+            A[k] = (int32_t)Ak; Bc[k] = (int32_t)Bk; q_abs[k] = Cpp >> 8;
         }
-        double gq[3][3], gs[3], gz[3];
-        if (ok) ok = exact::planes_double(p, d.H, d.W, gq, gs, gz);
-        if (ok) {
-            if (hard) {
-                kind = 2;
-                cmin = 0; cmax = d.W - 1; rmin = 0; rmax = d.H - 1;
-            } else {
-                const int64_t ax = xi[0], ay = yi[0], bx = xi[1], by = yi[1], cx = xi[2], cy = yi[2];
-                const int64_t area2 = (bx - ax) * (cy - ay) - (cx - ax) * (by - ay);
-                if (area2 == 0) ok = false;
-                else {
-                    int32_t px[3] = {xi[0], xi[1], xi[2]}, py[3] = {yi[0], yi[1], yi[2]};
-                    if (area2 < 0) {
-                        int32_t t = px[1]; px[1] = px[2]; px[2] = t;
-                        t = py[1]; py[1] = py[2]; py[2] = t;
-                    }
-                    int32_t A[3], Bc[3];
-                    int64_t q[3];
-#pragma unroll
-                    for (int k = 0; k < 3; ++k) {
-                        const int a = (k + 1) % 3, bb = (k + 2) % 3;
-                        const int64_t Ak = (int64_t)py[a] - py[bb];
-                        const int64_t Bk = (int64_t)px[bb] - px[a];
-                        const int64_t Ck = -(Ak * px[a] + Bk * py[a]);
-                        const bool tl = (Ak > 0) || (Ak == 0 && Bk > 0);
-                        const int64_t Cpp = 128 * (Ak + Bk) + Ck - (tl ? 0 : 1);
-                        A[k] = (int32_t)Ak; Bc[k] = (int32_t)Bk; q[k] = Cpp >> 8;
-                    }
-                    const int32_t xmin = min(px[0], min(px[1], px[2])), xmax = max(px[0], max(px[1], px[2]));
-                    const int32_t ymin = min(py[0], min(py[1], py[2])), ymax = max(py[0], max(py[1], py[2]));
-                    cmin = max((xmin + 127) >> 8, 0); cmax = min((xmax - 128) >> 8, d.W - 1);
-                    rmin = max((ymin + 127) >> 8, 0); rmax = min((ymax - 128) >> 8, d.H - 1);
-                    if (cmin > cmax || rmin > rmax) ok = false;
-                    else {
-                        kind = 1;
-                        cov.A0 = A[0]; cov.B0 = Bc[0]; cov.A1 = A[1]; cov.B1 = Bc[1]; cov.A2 = A[2]; cov.B2 = Bc[2];
-                        q_abs[0] = q[0]; q_abs[1] = q[1]; q_abs[2] = q[2];
-                    }
-                }
-            }
-        }
-        if (ok) {
-            const int cref = (kind == 1) ? cmin : 0, rref = (kind == 1) ? rmin : 0;
-            const double cr = (double)cref, rr = (double)rref;
-            zpl[0] = (float)gz[0]; zpl[1] = (float)gz[1]; zpl[2] = (float)gz[2];
-            itp.q0A = (float)gq[0][0]; itp.q0B = (float)gq[0][1];
-            itp.q0C = (float)__dadd_rn(__dadd_rn(__dmul_rn(gq[0][0], cr), __dmul_rn(gq[0][1], rr)), gq[0][2]);
-            itp.q1A = (float)gq[1][0]; itp.q1B = (float)gq[1][1];
-            itp.q1C = (float)__dadd_rn(__dadd_rn(__dmul_rn(gq[1][0], cr), __dmul_rn(gq[1][1], rr)), gq[1][2]);
-            itp.sA = (float)gs[0]; itp.sB = (float)gs[1];
-            itp.sC = (float)__dadd_rn(__dadd_rn(__dmul_rn(gs[0], cr), __dmul_rn(gs[1], rr)), gs[2]);
-            itp.v0 = vid[0]; itp.v1 = vid[1]; itp.v2 = vid[2];
-            itp.cref = cref; itp.rref = rref;
-        }
-    }
-    if (!ok) kind = 0;
-
-    // tile bounding box and the layout of the coverage record
-    int tx0 = 0, tx1 = -1, ty0 = 0, ty1 = -1;
-    bool small = false;
-    if (kind != 0) {
-        tx0 = cmin >> TILE_W_SHIFT; tx1 = cmax >> TILE_W_SHIFT;
-        ty0 = rmin >> TILE_H_SHIFT; ty1 = rmax >> TILE_H_SHIFT;
-        // "small" faces are binned per tile and rasterised entirely in int32: that needs a bounded tile count AND bounded
-        // edge coefficients (a huge, mostly off-screen face can have a small clamped bbox): |A|,|B| < 2^18, |q_rel| < 2^29
-        // keep q_rel + A*dcol + B*drow (|dcol|,|drow| < 2^9 inside the binned tiles) below 2^31.
-        const int64_t q0r = q_abs[0] + (int64_t)cov.A0 * cmin + (int64_t)cov.B0 * rmin;
-        const int64_t q1r = q_abs[1] + (int64_t)cov.A1 * cmin + (int64_t)cov.B1 * rmin;
-        const int64_t q2r = q_abs[2] + (int64_t)cov.A2 * cmin + (int64_t)cov.B2 * rmin;
-        const int32_t cmax_abs = max(max(max(abs(cov.A0), abs(cov.B0)), max(abs(cov.A1), abs(cov.B1))), max(abs(cov.A2), abs(cov.B2)));
-        const int64_t qlim = (int64_t)1 << 29;
-        small = kind == 1 && (tx1 - tx0 + 1) * (ty1 - ty0 + 1) <= SMALL_TILE_LIMIT && cmax_abs < (1 << 18) &&
-                q0r > -qlim && q0r < qlim && q1r > -qlim && q1r < qlim && q2r > -qlim && q2r < qlim;
-        if (small) {
-            cov.s.kind = KIND_SMALL;
-            cov.s.q0r = (int32_t)q0r; cov.s.q1r = (int32_t)q1r; cov.s.q2r = (int32_t)q2r;
-            cov.s.zA = zpl[0]; cov.s.zB = zpl[1]; cov.s.zC = zpl[2];
-            cov.s.cref = cmin; cov.s.rref = rmin; cov.s.pad = 0;
-        } else {
-            cov.s.kind = (kind == 2) ? KIND_HARD : KIND_LARGE;
-            cov.l.q0 = q_abs[0]; cov.l.q1 = q_abs[1]; cov.l.q2 = q_abs[2];
-            cov.l.zA = zpl[0]; cov.l.zB = zpl[1]; cov.l.zC = zpl[2];
-        }
+        const int32_t xmin = min(px[0], min(px[1], px[2])), xmax = max(px[0], max(px[1], px[2]));
+        const int32_t ymin = min(py[0], min(py[1], py[2])), ymax = max(py[0], max(py[1], py[2]));
+        cmin = max((xmin + 127) >> 8, 0); cmax = min((xmax - 128) >> 8, d.W - 1);
+        rmin = max((ymin + 127) >> 8, 0); rmax = min((ymax - 128) >> 8, d.H - 1);
+        if (cmin > cmax || rmin > rmax) { cull(); return; }
     }
 
-    // records (64-B stores as 4 x 16 B)
+    // interpolation record: planes relative to the bbox corner of a normal face (absolute for a hard one)
+    const int cref = hard ? 0 : cmin, rref = hard ? 0 : rmin;
     {
-        union { TriCov t; uint4 u[4]; } c; c.t = cov;
-        uint4* dst = reinterpret_cast<uint4*>(ws.cov + gid);
-        dst[0] = c.u[0]; dst[1] = c.u[1]; dst[2] = c.u[2]; dst[3] = c.u[3];
+        const double cr = (double)cref, rr = (double)rref;
+        TriInterp itp;
+        itp.q0A = (float)gq[0][0]; itp.q0B = (float)gq[0][1];
+        itp.q0C = (float)__dadd_rn(__dadd_rn(__dmul_rn(gq[0][0], cr), __dmul_rn(gq[0][1], rr)), gq[0][2]);
+        itp.q1A = (float)gq[1][0]; itp.q1B = (float)gq[1][1];
+        itp.q1C = (float)__dadd_rn(__dadd_rn(__dmul_rn(gq[1][0], cr), __dmul_rn(gq[1][1], rr)), gq[1][2]);
+        itp.sA = (float)gs[0]; itp.sB = (float)gs[1];
+        itp.sC = (float)__dadd_rn(__dadd_rn(__dmul_rn(gs[0], cr), __dmul_rn(gs[1], rr)), gs[2]);
+        itp.v0 = vid[0]; itp.v1 = vid[1]; itp.v2 = vid[2];
+        itp.cref = cref; itp.rref = rref;
+        itp.pad0 = itp.pad1 = 0;
         union { TriInterp t; uint4 u[4]; } i; i.t = itp;
         uint4* dsti = reinterpret_cast<uint4*>(ws.itp + gid);
         dsti[0] = i.u[0]; dsti[1] = i.u[1]; dsti[2] = i.u[2]; dsti[3] = i.u[3];
     }
+
+    // tile bounding box and the layout of the coverage record.
+    // "small" faces are binned per tile and rasterised entirely in int32: that needs a bounded tile count AND bounded
+    // edge coefficients (a huge, mostly off-screen face can have a small clamped bbox): |A|,|B| < 2^18, |q_rel| < 2^29
+    // keep q_rel + A*dcol + B*drow (|dcol|,|drow| < 2^9 inside the binned tiles) below 2^31.
+    const int tx0 = cmin >> TILE_W_SHIFT, tx1 = cmax >> TILE_W_SHIFT;
+    const int ty0 = rmin >> TILE_H_SHIFT, ty1 = rmax >> TILE_H_SHIFT;
+    const int64_t q0r = q_abs[0] + (int64_t)A[0] * cmin + (int64_t)Bc[0] * rmin;
+    const int64_t q1r = q_abs[1] + (int64_t)A[1] * cmin + (int64_t)Bc[1] * rmin;
+    const int64_t q2r = q_abs[2] + (int64_t)A[2] * cmin + (int64_t)Bc[2] * rmin;
+    const int32_t cmax_abs = max(max(max(abs(A[0]), abs(Bc[0])), max(abs(A[1]), abs(Bc[1]))), max(abs(A[2]), abs(Bc[2])));
+    const int64_t qlim = (int64_t)1 << 29;
+    const bool small = !hard && (tx1 - tx0 + 1) * (ty1 - ty0 + 1) <= SMALL_TILE_LIMIT && cmax_abs < (1 << 18) &&
+                       q0r > -qlim && q0r < qlim && q1r > -qlim && q1r < qlim && q2r > -qlim && q2r < qlim;
+    {
+        TriCov cov;
+        cov.A0 = A[0]; cov.B0 = Bc[0]; cov.A1 = A[1]; cov.B1 = Bc[1]; cov.A2 = A[2]; cov.B2 = Bc[2];
+        const float zA = (float)gz[0], zB = (float)gz[1], zC = (float)gz[2];
+        if (small) {
+            cov.s.kind = KIND_SMALL;
+            cov.s.q0r = (int32_t)q0r; cov.s.q1r = (int32_t)q1r; cov.s.q2r = (int32_t)q2r;
+            cov.s.zA = zA; cov.s.zB = zB; cov.s.zC = zC;
+            cov.s.cref = cmin; cov.s.rref = rmin; cov.s.pad = 0;
+        } else {
+            cov.l.kind = hard ? KIND_HARD : KIND_LARGE;
+            cov.l.q0 = q_abs[0]; cov.l.q1 = q_abs[1]; cov.l.q2 = q_abs[2];
+            cov.l.zA = zA; cov.l.zB = zB; cov.l.zC = zC;
+        }
+        union { TriCov t; uint4 u[4]; } c; c.t = cov;
+        uint4* dst = reinterpret_cast<uint4*>(ws.cov + gid);
+        dst[0] = c.u[0]; dst[1] = c.u[1]; dst[2] = c.u[2]; dst[3] = c.u[3];
+    }
     if (!BIN) return;
 
-    if (kind != 0) {
-        if (small) {
-            bin = make_uint2((uint32_t)tx0 | ((uint32_t)ty0 << 16), (uint32_t)tx1 | ((uint32_t)ty1 << 16));
-            int* counts = ws.tile_count + (size_t)b * d.tiles;
-            for (int ty = ty0; ty <= ty1; ++ty)
-                for (int tx = tx0; tx <= tx1; ++tx) atomicAdd(&counts[ty * d.tiles_x + tx], 1);
-        } else {
-            const int pos = atomicAdd(&ws.large_count[b], 1);
-            ws.large_list[(size_t)b * d.F + pos] = f;
-        }
+    if (small) {
+        ws.tri_bin[gid] = make_uint2((uint32_t)tx0 | ((uint32_t)ty0 << 16), (uint32_t)tx1 | ((uint32_t)ty1 << 16));
+        int* counts = ws.tile_count + (size_t)b * d.tiles;
+        for (int ty = ty0; ty <= ty1; ++ty)
+            for (int tx = tx0; tx <= tx1; ++tx) atomicAdd(&counts[ty * d.tiles_x + tx], 1);
+    } else {
+        ws.tri_bin[gid] = make_uint2(0xFFFFFFFFu, 0xFFFFFFFFu);
+        const int pos = atomicAdd(&ws.large_count[b], 1);
+        ws.large_list[(size_t)b * d.F + pos] = f;
     }
-    ws.tri_bin[gid] = bin;
 }
 
 // per-tile counts -> (offset,count); zeroes the count so fill_kernel can reuse it as a cursor
