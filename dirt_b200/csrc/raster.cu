@@ -21,11 +21,11 @@
 namespace dirt {
 
 #ifndef DIRT_RASTER_WARPS
-#define DIRT_RASTER_WARPS 4
-#endif
+#define DIRT_RASTER_WARPS 1   // one warp per CTA, 32 CTAs per SM: measured best (profiles/r01_sweep_warps2.txt) -- tiles retire
+#endif                        // independently and the shared-memory slot addresses are compile-time constants
 constexpr int WARPS_PER_BLOCK = DIRT_RASTER_WARPS;
 #ifndef DIRT_RASTER_MIN_BLOCKS
-#define DIRT_RASTER_MIN_BLOCKS 8   // <= 64 registers: measured best (profiles/r01_sweep_bounds.txt)
+#define DIRT_RASTER_MIN_BLOCKS 32   // x 32 threads: <= 64 registers, measured best (profiles/r01_sweep_bounds.txt, _warps2.txt)
 #endif
 
 struct __align__(16) Slot {
