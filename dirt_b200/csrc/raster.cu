@@ -255,13 +255,35 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, DIRT_RASTER_MIN_BLOCKS) 
     const TriInterp* itp_b = ws.itp + (size_t)b * d.F;
     const float* verts = vertices + (size_t)b * d.V * 4;
 
+    const int2 range = ws.tile_range[(size_t)b * d.tiles + t];
+    const int nlarge = ws.large_count[b];
+    const int col0 = tcol0 + (lane & 7) * 2, row0 = trow0 + (lane >> 3) * 2;
+    const size_t p00 = ((size_t)b * d.H + row0) * d.W + col0;   // pixel (row0, col0); the quad is p00 + {0, 1, W, W+1}
+    const bool whole = tcol0 + TILE_W <= d.W && trow0 + TILE_H <= d.H;   // warp-uniform: no per-pixel bounds checks
+    const int C = (CT > 0) ? CT : d.C;
+
+    // ---- nothing binned to this tile: the background passes through ----------------------------------------
+    if (range.y == 0 && nlarge == 0) {
+#pragma unroll
+        for (int pix = 0; pix < 4; ++pix) {
+            if (!whole && (row0 + (pix >> 1) >= d.H || col0 + (pix & 1) >= d.W)) continue;
+            const size_t p = p00 + (size_t)(pix >> 1) * d.W + (pix & 1);
+            if (face_ids_out) face_ids_out[p] = -1;
+            if (MODE == 1) {
+                if (gbuffer_out) reinterpret_cast<float4*>(gbuffer_out)[p] = make_float4(-1.f, -1.f, -1.f, __int_as_float(0x7f800000));
+            } else if (CT == 4) {
+                reinterpret_cast<float4*>(pixels)[p] = __ldg(reinterpret_cast<const float4*>(background) + p);
+            } else {
+                for (int ch = 0; ch < C; ++ch) pixels[p * C + ch] = __ldg(&background[p * C + ch]);
+            }
+        }
+        continue;
+    }
+
     Quad quad;
 #pragma unroll
     for (int i = 0; i < 4; ++i) quad.best[i] = pack(KEY_EMPTY, 0);
     uint32_t tile_max = KEY_EMPTY;
-
-    const int2 range = ws.tile_range[(size_t)b * d.tiles + t];
-    const int nlarge = ws.large_count[b];
     if (range.y > 0)
         consume_list<true>(ws.refs + range.x, range.y, cov_b, itp_b, verts, slots_all[warp], lane, tcol0, trow0, d.H, d.W,
                            quad, tile_max);
@@ -280,18 +302,16 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, DIRT_RASTER_MIN_BLOCKS) 
         }
     }
 
-    const int col0 = tcol0 + (lane & 7) * 2, row0 = trow0 + (lane >> 3) * 2;
-    const int C = (CT > 0) ? CT : d.C;
     const float* cols = vertex_colors + (size_t)b * d.V * C;
     int prev_face = -1;
     TriInterp ti;
 #pragma unroll
     for (int pix = 0; pix < 4; ++pix) {
         const int row = row0 + (pix >> 1), col = col0 + (pix & 1);
-        if (row >= d.H || col >= d.W) continue;
+        if (!whole && (row >= d.H || col >= d.W)) continue;
         const bool covered = (uint32_t)(quad.best[pix] >> 32) < KEY_EMPTY;
         const int face = covered ? (int)(uint32_t)quad.best[pix] : -1;
-        const size_t p = ((size_t)b * d.H + row) * d.W + col;
+        const size_t p = p00 + (size_t)(pix >> 1) * d.W + (pix & 1);
         if (face_ids_out) face_ids_out[p] = face;
         if (MODE == 1) {
             if (gbuffer_out) {
