@@ -23,6 +23,9 @@ constexpr int BWD_WARPS_PER_BLOCK = DIRT_BWD_WARPS;
 #ifndef DIRT_BWD_SMALL_LANES
 #define DIRT_BWD_SMALL_LANES 0  // > 0: the criterion is the number of lanes holding a record of the face instead
 #endif
+#ifndef DIRT_BWD_PREFETCH_GP
+#define DIRT_BWD_PREFETCH_GP 1   // measured: 0.429 -> 0.419 ms at cfg3 (profiles/r01_sweep_prefetch2.txt)
+#endif
 #ifndef DIRT_BWD_MIN_BLOCKS
 #define DIRT_BWD_MIN_BLOCKS 8   // <= 64 registers: measured best (profiles/r01_sweep_bounds.txt)
 #endif
@@ -465,6 +468,11 @@ __global__ void __launch_bounds__(BWD_WARPS_PER_BLOCK * 32, DIRT_BWD_MIN_BLOCKS)
     const size_t img = (size_t)b * H * W;
     const float halfW = 0.5f * (float)W, halfH = 0.5f * (float)H;
 
+#if DIRT_BWD_PREFETCH_GP
+    // start the DRAM read of this tile's grad_pixels while the tile flag is still on its way
+    if (C == 4 && lane < 8 && trow0 + lane < H && tcol0 < W)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(grad_pixels + (img + (size_t)(trow0 + lane) * W + tcol0) * 4));
+#endif
     // ---- background-only tiles: the forward pass flagged every 16x8 tile that shows a face or touches one that does.
     // Nothing can reach an unflagged tile: grad_background = grad_pixels and we are done.
     if (tile_flags != nullptr && tile_flags[(size_t)b * d.tiles + ty * d.tiles_x + (tx >> 1)] == 0) {

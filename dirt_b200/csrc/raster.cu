@@ -24,6 +24,9 @@ namespace dirt {
 #define DIRT_RASTER_WARPS 1   // one warp per CTA, 32 CTAs per SM: measured best (profiles/r01_sweep_warps2.txt) -- tiles retire
 #endif                        // independently and the shared-memory slot addresses are compile-time constants
 constexpr int WARPS_PER_BLOCK = DIRT_RASTER_WARPS;
+#ifndef DIRT_RASTER_PREFETCH_BG
+#define DIRT_RASTER_PREFETCH_BG 0
+#endif
 #ifndef DIRT_RASTER_MIN_BLOCKS
 #define DIRT_RASTER_MIN_BLOCKS 32   // x 32 threads: <= 64 registers, measured best (profiles/r01_sweep_bounds.txt, _warps2.txt)
 #endif
@@ -255,6 +258,15 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, DIRT_RASTER_MIN_BLOCKS) 
     const TriInterp* itp_b = ws.itp + (size_t)b * d.F;
     const float* verts = vertices + (size_t)b * d.V * 4;
 
+#if DIRT_RASTER_PREFETCH_BG
+    // Pull this tile's background lines towards L2 while the tile's list range is still on its way: tiles that show
+    // no face (most of a frame) otherwise wait for the range and only then start the DRAM read of the background.
+    if (MODE == 0 && CT == 4 && lane < 16) {
+        const int r = trow0 + (lane >> 1), c = tcol0 + (lane & 1) * 8;
+        if (r < d.H && c < d.W)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(background + (((size_t)b * d.H + r) * d.W + c) * 4));
+    }
+#endif
     const int2 range = ws.tile_range[(size_t)b * d.tiles + t];
     const int nlarge = ws.large_count[b];
     const int col0 = tcol0 + (lane & 7) * 2, row0 = trow0 + (lane >> 3) * 2;
