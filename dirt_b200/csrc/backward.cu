@@ -259,20 +259,24 @@ __device__ __forceinline__ Fragment dilate(const Fragment& own, int code, const 
                                            const TriInterp* __restrict__ itp_b, int col, int row, int& src)
 {
     src = 0;
+    // code = +-1: the horizontal pair (right, left); +-3: the vertical pair (up, down).  The first attempt looks along
+    // the sign of `code`, the second one the other way.
+    const bool horiz = (unsigned)(code + 1) <= 2u;
+    const int f_plus = horiz ? nb.right : nb.up, f_minus = horiz ? nb.left : nb.down;
 #pragma unroll
     for (int attempt = 0; attempt < 2; ++attempt) {
-        // buffer offset (dx,dy) is image (col + dx, row - dy)
-        const int fn = (code == 1) ? nb.right : (code == -1) ? nb.left : (code == 3) ? nb.up : nb.down;
+        const bool minus = (code < 0) != (attempt == 1);
+        const int fn = minus ? f_minus : f_plus;
         if (fn >= 0 && fn != own.face) {
-            const int dx = (code == 1) - (code == -1), dy = (code == 3) - (code == -3);
-            const Fragment n = fragment_at(itp_b, fn, col + dx, row - dy);
+            // buffer offset (dx,dy) is image (col + dx, row - dy)
+            const int step = minus ? -1 : 1;
+            const Fragment n = fragment_at(itp_b, fn, horiz ? col + step : col, horiz ? row : row - step);
             const bool differs = (own.face < 0) || n.v0 != own.v0 || n.v1 != own.v1 || n.v2 != own.v2;
             if (differs && own.g.w > n.g.w) {
-                src = code;   // distinguishes the four neighbours, never 0
+                src = attempt ? -code : code;   // distinguishes the four neighbours, never 0
                 return n;
             }
         }
-        code = -code;
     }
     return own;
 }
