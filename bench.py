@@ -216,6 +216,20 @@ class HostStep:
     def step(self):
         return self.runner.step(**self.h_in)
 
+    def copies_only(self):
+        """The transfers of one step with no kernels: all inputs host->device on one stream while all outputs go
+        device->host on another (PCIe is full duplex) -- the floor under the end-to-end time of this box."""
+        torch, r = self.p.torch, self.runner
+        cur = torch.cuda.current_stream(r.device)
+        r.s_in.wait_stream(cur); r.s_out.wait_stream(cur)
+        with torch.cuda.stream(r.s_in):
+            for k, t in self.h_in.items():
+                r.d[k].copy_(t, non_blocking=True)
+        with torch.cuda.stream(r.s_out):
+            for k, t in r.h_out.items():
+                t.copy_(r.d[k], non_blocking=True)
+        cur.wait_stream(r.s_in); cur.wait_stream(r.s_out)
+
 
 def cpu_baseline(scene, grad_pixels, sample_images, threads=None, min_seconds=10.0):
     """fwd+bwd of the CPU oracle (a port of the reference path) on `sample_images` images of the workload,
@@ -366,8 +380,19 @@ def run_ours(args):
         if world > 1:
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
         e2e_ms = float(te.item())
+        # the transfers alone (same buffers, no kernels): what the PCIe link of this box allows
+        host.copies_only()
+        sync_all()
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record()
+        for _ in range(n_e2e):
+            host.copies_only()
+        c1.record()
+        sync_all()
+        copy_ms = c0.elapsed_time(c1) / n_e2e
         e2e = {'value': world * B * H * W / (e2e_ms * 1e-3) / 1e6, 'unit': UNIT, 'ms_per_step': e2e_ms,
-               'h2d_bytes_per_step': int(host.h2d), 'd2h_bytes_per_step': int(host.d2h)}
+               'h2d_bytes_per_step': int(host.h2d), 'd2h_bytes_per_step': int(host.d2h),
+               'transfers_only_ms': copy_ms, 'chunks': int(host.runner.chunks)}
         del host
 
     if rank != 0:

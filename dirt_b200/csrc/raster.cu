@@ -24,6 +24,10 @@ namespace dirt {
 #define DIRT_RASTER_WARPS 1   // one warp per CTA, 32 CTAs per SM: measured best (profiles/r01_sweep_warps2.txt) -- tiles retire
 #endif                        // independently and the shared-memory slot addresses are compile-time constants
 constexpr int WARPS_PER_BLOCK = DIRT_RASTER_WARPS;
+#ifndef DIRT_RASTER_TILES
+#define DIRT_RASTER_TILES 2   // tiles (neighbours in x) per warp: measured 0.167 -> 0.152 ms at cfg3 (empty pairs are copied together)
+#endif
+constexpr int TILES_PER_WARP = DIRT_RASTER_TILES;
 #ifndef DIRT_RASTER_PREFETCH_BG
 #define DIRT_RASTER_PREFETCH_BG 0
 #endif
@@ -246,17 +250,46 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, DIRT_RASTER_MIN_BLOCKS) 
     float* __restrict__ gbuffer_out, Workspace ws, Dims d)
 {
     __shared__ Slot slots_all[WARPS_PER_BLOCK][32];
-    // grid: x = groups of WARPS_PER_BLOCK tiles along a tile row, y = tile row, z = image
+    // grid: x = groups of WARPS_PER_BLOCK * TILES_PER_WARP tiles along a tile row, y = tile row, z = image
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int tx = blockIdx.x * WARPS_PER_BLOCK + warp, ty = blockIdx.y;
-    if (tx >= d.tiles_x) return;
-    const int t = ty * d.tiles_x + tx;
-    const int tcol0 = tx * TILE_W, trow0 = ty * TILE_H;
+    const int txb = (blockIdx.x * WARPS_PER_BLOCK + warp) * TILES_PER_WARP, ty = blockIdx.y;
+    if (txb >= d.tiles_x) return;
+    const int trow0 = ty * TILE_H;
     for (int b = blockIdx.z; b < d.B; b += gridDim.z) {   // gridDim.z == B unless B exceeds the grid limit
 
     const TriCov* cov_b = ws.cov + (size_t)b * d.F;
     const TriInterp* itp_b = ws.itp + (size_t)b * d.F;
     const float* verts = vertices + (size_t)b * d.V * 4;
+
+#if DIRT_RASTER_TILES == 2
+    // Two neighbouring tiles with nothing binned to either (most of a frame): one pass with both tiles' loads in
+    // flight -- an empty tile is pure latency (range -> background -> store), so this doubles the bytes per resident warp.
+    if (MODE == 0 && CT == 4 && txb + 1 < d.tiles_x && (txb + 2) * TILE_W <= d.W && trow0 + TILE_H <= d.H) {
+        const int2* rp = ws.tile_range + (size_t)b * d.tiles + ty * d.tiles_x + txb;
+        const int2 ra = rp[0], rb = rp[1];
+        if (ra.y == 0 && rb.y == 0 && ws.large_count[b] == 0) {
+            const int col0 = txb * TILE_W + (lane & 7) * 2, row0 = trow0 + (lane >> 3) * 2;
+            const size_t p00 = ((size_t)b * d.H + row0) * d.W + col0;
+            const float4* src = reinterpret_cast<const float4*>(background);
+            float4* dst = reinterpret_cast<float4*>(pixels);
+            float4 v[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = __ldg(src + p00 + (size_t)((i >> 1) & 1) * d.W + (i & 1) + (i >> 2) * TILE_W);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const size_t p = p00 + (size_t)((i >> 1) & 1) * d.W + (i & 1) + (i >> 2) * TILE_W;
+                dst[p] = v[i];
+                if (face_ids_out) face_ids_out[p] = -1;
+            }
+            continue;
+        }
+    }
+#endif
+    for (int sub = 0; sub < TILES_PER_WARP; ++sub) {
+    const int tx = txb + sub;
+    if (tx >= d.tiles_x) break;
+    const int t = ty * d.tiles_x + tx;
+    const int tcol0 = tx * TILE_W;
 
 #if DIRT_RASTER_PREFETCH_BG
     // Pull this tile's background lines towards L2 while the tile's list range is still on its way: tiles that show
@@ -342,7 +375,8 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, DIRT_RASTER_MIN_BLOCKS) 
             shade_pixel<CT>(ti, col, row, cols, pixels + p * C, C);
         }
     }
-    }
+    }   // sub
+    }   // b
 }
 
 cudaError_t launch_raster_forward(const float* vertices, const float* background, const float* vertex_colors, float* pixels,
@@ -350,7 +384,7 @@ cudaError_t launch_raster_forward(const float* vertices, const float* background
                                   int* launches)
 {
     if ((long long)d.B * d.tiles == 0) return cudaSuccess;
-    const dim3 grid((unsigned)((d.tiles_x + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK), (unsigned)d.tiles_y, (unsigned)min(d.B, 65535));
+    const dim3 grid((unsigned)((d.tiles_x + WARPS_PER_BLOCK * TILES_PER_WARP - 1) / (WARPS_PER_BLOCK * TILES_PER_WARP)), (unsigned)d.tiles_y, (unsigned)min(d.B, 65535));
     ScopedKernelTimer timer(1, stream);
     const bool vec4 = d.C == 4 && ((uintptr_t)background % 16 == 0) && ((uintptr_t)pixels % 16 == 0) &&
                       ((uintptr_t)vertex_colors % 16 == 0);
@@ -368,7 +402,7 @@ cudaError_t launch_raster_visibility(const float* vertices, int32_t* face_ids, f
                                      cudaStream_t stream, int* launches)
 {
     if ((long long)d.B * d.tiles == 0) return cudaSuccess;
-    const dim3 grid((unsigned)((d.tiles_x + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK), (unsigned)d.tiles_y, (unsigned)min(d.B, 65535));
+    const dim3 grid((unsigned)((d.tiles_x + WARPS_PER_BLOCK * TILES_PER_WARP - 1) / (WARPS_PER_BLOCK * TILES_PER_WARP)), (unsigned)d.tiles_y, (unsigned)min(d.B, 65535));
     raster_kernel<1, 0><<<grid, WARPS_PER_BLOCK * 32, 0, stream>>>(vertices, nullptr, nullptr, nullptr, face_ids, gbuffer, ws, d);
     ++*launches;
     return cudaGetLastError();
