@@ -23,6 +23,16 @@ constexpr int BWD_WARPS_PER_BLOCK = DIRT_BWD_WARPS;
 #ifndef DIRT_BWD_SMALL_LANES
 #define DIRT_BWD_SMALL_LANES 0  // > 0: the criterion is the number of lanes holding a record of the face instead
 #endif
+// 8x8 tiles (neighbours in x, = one 16x8 tile of the coverage flags) per warp.  Measured (profiles/r01_sweep_bwd_tiles.txt):
+// pairs win for C = 3 (cfg5 backward 1.36 -> 1.26 ms: a background-only pair is copied with both tiles' loads in flight)
+// and lose for C = 4, whose larger per-pixel state spills more when the tile body sits in a loop.
+#ifndef DIRT_BWD_TILES_C4
+#define DIRT_BWD_TILES_C4 1
+#endif
+#ifndef DIRT_BWD_TILES_C3
+#define DIRT_BWD_TILES_C3 2
+#endif
+template <int C> struct BwdTiles { static constexpr int value = (C == 4) ? DIRT_BWD_TILES_C4 : DIRT_BWD_TILES_C3; };
 #ifndef DIRT_BWD_PREFETCH_GP
 #define DIRT_BWD_PREFETCH_GP 1   // measured: 0.429 -> 0.419 ms at cfg3 (profiles/r01_sweep_prefetch2.txt)
 #endif
@@ -440,7 +450,7 @@ __device__ __forceinline__ int owner_meta(int lane)
     return C == 1 ? c_owner1.meta[lane] : C == 3 ? c_owner3.meta[lane] : c_owner4.meta[lane];
 }
 
-template <int C>
+template <int C, int BWD_TILES>
 __global__ void __launch_bounds__(BWD_WARPS_PER_BLOCK * 32, DIRT_BWD_MIN_BLOCKS) backward_tile_kernel(
     const float* __restrict__ vertices, const float* __restrict__ pixels, const float* __restrict__ grad_pixels,
     const int32_t* __restrict__ face_ids, float* __restrict__ grad_background, float* __restrict__ grad_vertices,
@@ -453,13 +463,13 @@ __global__ void __launch_bounds__(BWD_WARPS_PER_BLOCK * 32, DIRT_BWD_MIN_BLOCKS)
 
     __shared__ __align__(16) float tile_all[BWD_WARPS_PER_BLOCK][HALO_ROWS * HALO_COLS * C];
 
-    // grid: x = groups of BWD_WARPS_PER_BLOCK tiles along a tile row, y = tile row, z = image
+    // grid: x = groups of BWD_WARPS_PER_BLOCK * BWD_TILES tiles along a tile row, y = tile row, z = image
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int tx = blockIdx.x * BWD_WARPS_PER_BLOCK + warp, ty = blockIdx.y;
-    if (tx >= d.btiles_x) return;
-    const int tcol0 = tx * TILE, trow0 = ty * TILE;
+    const int txb = (blockIdx.x * BWD_WARPS_PER_BLOCK + warp) * BWD_TILES, ty = blockIdx.y;
+    if (txb >= d.btiles_x) return;
+    const int trow0 = ty * TILE;
     const int lcol = lane & 7, lrow0 = (lane >> 3) * 2;
-    const int col = tcol0 + lcol, row0 = trow0 + lrow0;
+    const int row0 = trow0 + lrow0;
     const int H = d.H, W = d.W;
     float* tile = tile_all[warp];
 
@@ -472,6 +482,48 @@ __global__ void __launch_bounds__(BWD_WARPS_PER_BLOCK * 32, DIRT_BWD_MIN_BLOCKS)
     const size_t img = (size_t)b * H * W;
     const float halfW = 0.5f * (float)W, halfH = 0.5f * (float)H;
 
+    if (BWD_TILES == 2) {
+    // The two 8x8 tiles of this warp are exactly one 16x8 tile of the forward pass's coverage flags.
+#if DIRT_BWD_PREFETCH_GP
+    // start the DRAM read of the pair's grad_pixels while the flag is still on its way
+    if (C == 4 && lane < 16 && trow0 + (lane >> 1) < H && (txb + (lane & 1)) * TILE < W)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(grad_pixels + (img + (size_t)(trow0 + (lane >> 1)) * W + (txb + (lane & 1)) * TILE) * 4));
+#endif
+    // ---- background-only pair: nothing can reach an unflagged tile, grad_background = grad_pixels and we are done.
+    // Both tiles' loads are issued before the first store: such a pair is pure latency (flag -> load -> store).
+    if (tile_flags != nullptr && tile_flags[(size_t)b * d.tiles + ty * d.tiles_x + (txb >> 1)] == 0) {
+        if (C == 4) {
+            float4 v[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int row = row0 + (i & 1), col = (txb + (i >> 1)) * TILE + lcol;
+                if (col < W && row < H) v[i] = __ldg(reinterpret_cast<const float4*>(grad_pixels) + img + (size_t)row * W + col);
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int row = row0 + (i & 1), col = (txb + (i >> 1)) * TILE + lcol;
+                if (col < W && row < H) reinterpret_cast<float4*>(grad_background)[img + (size_t)row * W + col] = v[i];
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int row = row0 + (i & 1), col = (txb + (i >> 1)) * TILE + lcol;
+                if (col >= W || row >= H) continue;
+                const size_t p = img + (size_t)row * W + col;
+#pragma unroll
+                for (int ch = 0; ch < C; ++ch) grad_background[p * C + ch] = __ldg(grad_pixels + p * C + ch);
+            }
+        }
+        continue;
+    }
+    }
+    for (int sub = 0; sub < BWD_TILES; ++sub) {
+    const int tx = txb + sub;
+    if (tx >= d.btiles_x) break;
+    const int tcol0 = tx * TILE;
+    const int col = tcol0 + lcol;
+
+    if (BWD_TILES == 1) {
 #if DIRT_BWD_PREFETCH_GP
     // start the DRAM read of this tile's grad_pixels while the tile flag is still on its way
     if (C == 4 && lane < 8 && trow0 + lane < H && tcol0 < W)
@@ -492,6 +544,7 @@ __global__ void __launch_bounds__(BWD_WARPS_PER_BLOCK * 32, DIRT_BWD_MIN_BLOCKS)
             }
         }
         continue;
+    }
     }
 
     // ---- this lane's two pixels and their six outer neighbours in the visibility buffer; grad_pixels ------------
@@ -781,7 +834,8 @@ __global__ void __launch_bounds__(BWD_WARPS_PER_BLOCK * 32, DIRT_BWD_MIN_BLOCKS)
 #endif
     }
 #endif
-    }
+    }   // sub
+    }   // b
 }
 
 cudaError_t launch_backward(const float* vertices, const float* pixels, const float* grad_pixels,
@@ -802,17 +856,19 @@ cudaError_t launch_backward(const float* vertices, const float* pixels, const fl
                                         (uintptr_t)grad_vertex_colors) % 16 == 0);
     const dim3 block(BWD_WARPS_PER_BLOCK * 32);
     const unsigned char* flags = tile_flags_valid ? ws.tile_flags : nullptr;
-    const dim3 grid2((unsigned)((d.btiles_x + BWD_WARPS_PER_BLOCK - 1) / BWD_WARPS_PER_BLOCK), (unsigned)d.btiles_y,
-                     (unsigned)min(d.B, 65535));
+    auto grid_for = [&](int tiles_per_warp) {
+        return dim3((unsigned)((d.btiles_x + BWD_WARPS_PER_BLOCK * tiles_per_warp - 1) / (BWD_WARPS_PER_BLOCK * tiles_per_warp)),
+                    (unsigned)d.btiles_y, (unsigned)min(d.B, 65535));
+    };
     if (default_groups && aligned4 && d.C == 4)
-        backward_tile_kernel<4><<<grid2, block, 0, stream>>>(vertices, pixels, grad_pixels, face_ids, grad_background,
-                                                             grad_vertices, grad_vertex_colors, ws, d, flags);
+        backward_tile_kernel<4, BwdTiles<4>::value><<<grid_for(BwdTiles<4>::value), block, 0, stream>>>(
+            vertices, pixels, grad_pixels, face_ids, grad_background, grad_vertices, grad_vertex_colors, ws, d, flags);
     else if (default_groups && d.C == 3)
-        backward_tile_kernel<3><<<grid2, block, 0, stream>>>(vertices, pixels, grad_pixels, face_ids, grad_background,
-                                                             grad_vertices, grad_vertex_colors, ws, d, flags);
+        backward_tile_kernel<3, BwdTiles<3>::value><<<grid_for(BwdTiles<3>::value), block, 0, stream>>>(
+            vertices, pixels, grad_pixels, face_ids, grad_background, grad_vertices, grad_vertex_colors, ws, d, flags);
     else if (default_groups && d.C == 1)
-        backward_tile_kernel<1><<<grid2, block, 0, stream>>>(vertices, pixels, grad_pixels, face_ids, grad_background,
-                                                             grad_vertices, grad_vertex_colors, ws, d, flags);
+        backward_tile_kernel<1, BwdTiles<1>::value><<<grid_for(BwdTiles<1>::value), block, 0, stream>>>(
+            vertices, pixels, grad_pixels, face_ids, grad_background, grad_vertices, grad_vertex_colors, ws, d, flags);
     else {
         const unsigned grid = (unsigned)((total_tiles + BWD_WARPS_PER_BLOCK - 1) / BWD_WARPS_PER_BLOCK);
         backward_generic_kernel<<<grid, block, 0, stream>>>(vertices, pixels, grad_pixels, face_ids, grad_background,
