@@ -32,7 +32,17 @@ constexpr int BWD_WARPS_PER_BLOCK = DIRT_BWD_WARPS;
 #ifndef DIRT_BWD_TILES_C3
 #define DIRT_BWD_TILES_C3 2
 #endif
-template <int C> struct BwdTiles { static constexpr int value = (C == 4) ? DIRT_BWD_TILES_C4 : DIRT_BWD_TILES_C3; };
+// warps per CTA (32 warps per SM resident either way: 32 / warps CTAs of <= 64 registers per thread)
+#ifndef DIRT_BWD_WARPS_C4
+#define DIRT_BWD_WARPS_C4 DIRT_BWD_WARPS
+#endif
+#ifndef DIRT_BWD_WARPS_C3
+#define DIRT_BWD_WARPS_C3 DIRT_BWD_WARPS
+#endif
+template <int C> struct BwdTiles {
+    static constexpr int value = (C == 4) ? DIRT_BWD_TILES_C4 : DIRT_BWD_TILES_C3;
+    static constexpr int warps = (C == 4) ? DIRT_BWD_WARPS_C4 : DIRT_BWD_WARPS_C3;
+};
 #ifndef DIRT_BWD_PREFETCH_GP
 #define DIRT_BWD_PREFETCH_GP 1   // measured: 0.429 -> 0.419 ms at cfg3 (profiles/r01_sweep_prefetch2.txt)
 #endif
@@ -450,8 +460,8 @@ __device__ __forceinline__ int owner_meta(int lane)
     return C == 1 ? c_owner1.meta[lane] : C == 3 ? c_owner3.meta[lane] : c_owner4.meta[lane];
 }
 
-template <int C, int BWD_TILES>
-__global__ void __launch_bounds__(BWD_WARPS_PER_BLOCK * 32, DIRT_BWD_MIN_BLOCKS) backward_tile_kernel(
+template <int C, int BWD_TILES, int NW>
+__global__ void __launch_bounds__(NW * 32, DIRT_BWD_MIN_BLOCKS * DIRT_BWD_WARPS / NW) backward_tile_kernel(
     const float* __restrict__ vertices, const float* __restrict__ pixels, const float* __restrict__ grad_pixels,
     const int32_t* __restrict__ face_ids, float* __restrict__ grad_background, float* __restrict__ grad_vertices,
     float* __restrict__ grad_vertex_colors, Workspace ws, Dims d, const unsigned char* __restrict__ tile_flags)
@@ -461,11 +471,11 @@ __global__ void __launch_bounds__(BWD_WARPS_PER_BLOCK * 32, DIRT_BWD_MIN_BLOCKS)
     constexpr bool TWO_GROUPS = (C == 4);      // {3,1}
     constexpr int REACH = (C == 3) ? 1 : 3;    // columns to the right of the pixel that its taps read
 
-    __shared__ __align__(16) float tile_all[BWD_WARPS_PER_BLOCK][HALO_ROWS * HALO_COLS * C];
+    __shared__ __align__(16) float tile_all[NW][HALO_ROWS * HALO_COLS * C];
 
     // grid: x = groups of BWD_WARPS_PER_BLOCK * BWD_TILES tiles along a tile row, y = tile row, z = image
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int txb = (blockIdx.x * BWD_WARPS_PER_BLOCK + warp) * BWD_TILES, ty = blockIdx.y;
+    const int txb = (blockIdx.x * NW + warp) * BWD_TILES, ty = blockIdx.y;
     if (txb >= d.btiles_x) return;
     const int trow0 = ty * TILE;
     const int lcol = lane & 7, lrow0 = (lane >> 3) * 2;
@@ -856,19 +866,22 @@ cudaError_t launch_backward(const float* vertices, const float* pixels, const fl
                                         (uintptr_t)grad_vertex_colors) % 16 == 0);
     const dim3 block(BWD_WARPS_PER_BLOCK * 32);
     const unsigned char* flags = tile_flags_valid ? ws.tile_flags : nullptr;
-    auto grid_for = [&](int tiles_per_warp) {
-        return dim3((unsigned)((d.btiles_x + BWD_WARPS_PER_BLOCK * tiles_per_warp - 1) / (BWD_WARPS_PER_BLOCK * tiles_per_warp)),
-                    (unsigned)d.btiles_y, (unsigned)min(d.B, 65535));
+    auto grid_for = [&](int tiles_per_warp, int warps) {
+        return dim3((unsigned)((d.btiles_x + warps * tiles_per_warp - 1) / (warps * tiles_per_warp)), (unsigned)d.btiles_y,
+                    (unsigned)min(d.B, 65535));
     };
     if (default_groups && aligned4 && d.C == 4)
-        backward_tile_kernel<4, BwdTiles<4>::value><<<grid_for(BwdTiles<4>::value), block, 0, stream>>>(
-            vertices, pixels, grad_pixels, face_ids, grad_background, grad_vertices, grad_vertex_colors, ws, d, flags);
+        backward_tile_kernel<4, BwdTiles<4>::value, BwdTiles<4>::warps>
+            <<<grid_for(BwdTiles<4>::value, BwdTiles<4>::warps), BwdTiles<4>::warps * 32, 0, stream>>>(
+                vertices, pixels, grad_pixels, face_ids, grad_background, grad_vertices, grad_vertex_colors, ws, d, flags);
     else if (default_groups && d.C == 3)
-        backward_tile_kernel<3, BwdTiles<3>::value><<<grid_for(BwdTiles<3>::value), block, 0, stream>>>(
-            vertices, pixels, grad_pixels, face_ids, grad_background, grad_vertices, grad_vertex_colors, ws, d, flags);
+        backward_tile_kernel<3, BwdTiles<3>::value, BwdTiles<3>::warps>
+            <<<grid_for(BwdTiles<3>::value, BwdTiles<3>::warps), BwdTiles<3>::warps * 32, 0, stream>>>(
+                vertices, pixels, grad_pixels, face_ids, grad_background, grad_vertices, grad_vertex_colors, ws, d, flags);
     else if (default_groups && d.C == 1)
-        backward_tile_kernel<1, BwdTiles<1>::value><<<grid_for(BwdTiles<1>::value), block, 0, stream>>>(
-            vertices, pixels, grad_pixels, face_ids, grad_background, grad_vertices, grad_vertex_colors, ws, d, flags);
+        backward_tile_kernel<1, BwdTiles<1>::value, BwdTiles<1>::warps>
+            <<<grid_for(BwdTiles<1>::value, BwdTiles<1>::warps), BwdTiles<1>::warps * 32, 0, stream>>>(
+                vertices, pixels, grad_pixels, face_ids, grad_background, grad_vertices, grad_vertex_colors, ws, d, flags);
     else {
         const unsigned grid = (unsigned)((total_tiles + BWD_WARPS_PER_BLOCK - 1) / BWD_WARPS_PER_BLOCK);
         backward_generic_kernel<<<grid, block, 0, stream>>>(vertices, pixels, grad_pixels, face_ids, grad_background,

@@ -264,22 +264,39 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, DIRT_RASTER_MIN_BLOCKS) 
 #if DIRT_RASTER_TILES == 2
     // Two neighbouring tiles with nothing binned to either (most of a frame): one pass with both tiles' loads in
     // flight -- an empty tile is pure latency (range -> background -> store), so this doubles the bytes per resident warp.
-    if (MODE == 0 && CT == 4 && txb + 1 < d.tiles_x && (txb + 2) * TILE_W <= d.W && trow0 + TILE_H <= d.H) {
+    if (MODE == 0 && (CT == 4 || CT == 3) && txb + 1 < d.tiles_x && (txb + 2) * TILE_W <= d.W && trow0 + TILE_H <= d.H) {
         const int2* rp = ws.tile_range + (size_t)b * d.tiles + ty * d.tiles_x + txb;
         const int2 ra = rp[0], rb = rp[1];
         if (ra.y == 0 && rb.y == 0 && ws.large_count[b] == 0) {
             const int col0 = txb * TILE_W + (lane & 7) * 2, row0 = trow0 + (lane >> 3) * 2;
             const size_t p00 = ((size_t)b * d.H + row0) * d.W + col0;
-            const float4* src = reinterpret_cast<const float4*>(background);
-            float4* dst = reinterpret_cast<float4*>(pixels);
-            float4 v[8];
+            if (CT == 4) {
+                const float4* src = reinterpret_cast<const float4*>(background);
+                float4* dst = reinterpret_cast<float4*>(pixels);
+                float4 v[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) v[i] = __ldg(src + p00 + (size_t)((i >> 1) & 1) * d.W + (i & 1) + (i >> 2) * TILE_W);
+                for (int i = 0; i < 8; ++i) v[i] = __ldg(src + p00 + (size_t)((i >> 1) & 1) * d.W + (i & 1) + (i >> 2) * TILE_W);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const size_t p = p00 + (size_t)((i >> 1) & 1) * d.W + (i & 1) + (i >> 2) * TILE_W;
-                dst[p] = v[i];
-                if (face_ids_out) face_ids_out[p] = -1;
+                for (int i = 0; i < 8; ++i) dst[p00 + (size_t)((i >> 1) & 1) * d.W + (i & 1) + (i >> 2) * TILE_W] = v[i];
+            } else {
+                // CT == 3: the two pixels of a quad row are 24 contiguous, 8-byte aligned bytes (checked at launch)
+                const float2* src = reinterpret_cast<const float2*>(background);
+                float2* dst = reinterpret_cast<float2*>(pixels);
+                float2 v[12];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {   // i: bit 0 = row of the quad, bit 1 = tile of the pair
+                    const size_t q = (p00 + (size_t)(i & 1) * d.W + (i >> 1) * TILE_W) * 3 / 2;
+                    v[3 * i] = __ldg(src + q); v[3 * i + 1] = __ldg(src + q + 1); v[3 * i + 2] = __ldg(src + q + 2);
+                }
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const size_t q = (p00 + (size_t)(i & 1) * d.W + (i >> 1) * TILE_W) * 3 / 2;
+                    dst[q] = v[3 * i]; dst[q + 1] = v[3 * i + 1]; dst[q + 2] = v[3 * i + 2];
+                }
+            }
+            if (face_ids_out) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) face_ids_out[p00 + (size_t)((i >> 1) & 1) * d.W + (i & 1) + (i >> 2) * TILE_W] = -1;
             }
             continue;
         }
@@ -309,6 +326,23 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, DIRT_RASTER_MIN_BLOCKS) 
 
     // ---- nothing binned to this tile: the background passes through ----------------------------------------
     if (range.y == 0 && nlarge == 0) {
+        if (MODE == 0 && CT == 3 && whole) {
+            const float2* src = reinterpret_cast<const float2*>(background);
+            float2* dst = reinterpret_cast<float2*>(pixels);
+            float2 v[6];
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const size_t q = (p00 + (size_t)i * d.W) * 3 / 2;
+                v[3 * i] = __ldg(src + q); v[3 * i + 1] = __ldg(src + q + 1); v[3 * i + 2] = __ldg(src + q + 2);
+            }
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const size_t q = (p00 + (size_t)i * d.W) * 3 / 2;
+                dst[q] = v[3 * i]; dst[q + 1] = v[3 * i + 1]; dst[q + 2] = v[3 * i + 2];
+                if (face_ids_out) { face_ids_out[p00 + (size_t)i * d.W] = -1; face_ids_out[p00 + (size_t)i * d.W + 1] = -1; }
+            }
+            continue;
+        }
 #pragma unroll
         for (int pix = 0; pix < 4; ++pix) {
             if (!whole && (row0 + (pix >> 1) >= d.H || col0 + (pix & 1) >= d.W)) continue;
@@ -388,8 +422,13 @@ cudaError_t launch_raster_forward(const float* vertices, const float* background
     ScopedKernelTimer timer(1, stream);
     const bool vec4 = d.C == 4 && ((uintptr_t)background % 16 == 0) && ((uintptr_t)pixels % 16 == 0) &&
                       ((uintptr_t)vertex_colors % 16 == 0);
+    // C == 3 with an even width: every quad row (two pixels) is 24 contiguous, 8-byte aligned bytes
+    const bool vec3 = d.C == 3 && d.W % 2 == 0 && ((uintptr_t)background % 8 == 0) && ((uintptr_t)pixels % 8 == 0);
     if (vec4)
         raster_kernel<0, 4><<<grid, WARPS_PER_BLOCK * 32, 0, stream>>>(vertices, background, vertex_colors, pixels,
+                                                                       face_ids_out, nullptr, ws, d);
+    else if (vec3)
+        raster_kernel<0, 3><<<grid, WARPS_PER_BLOCK * 32, 0, stream>>>(vertices, background, vertex_colors, pixels,
                                                                        face_ids_out, nullptr, ws, d);
     else
         raster_kernel<0, 0><<<grid, WARPS_PER_BLOCK * 32, 0, stream>>>(vertices, background, vertex_colors, pixels,
