@@ -464,7 +464,8 @@ template <int C, int BWD_TILES, int NW>
 __global__ void __launch_bounds__(NW * 32, DIRT_BWD_MIN_BLOCKS * DIRT_BWD_WARPS / NW) backward_tile_kernel(
     const float* __restrict__ vertices, const float* __restrict__ pixels, const float* __restrict__ grad_pixels,
     const int32_t* __restrict__ face_ids, float* __restrict__ grad_background, float* __restrict__ grad_vertices,
-    float* __restrict__ grad_vertex_colors, Workspace ws, Dims d, const unsigned char* __restrict__ tile_flags)
+    float* __restrict__ grad_vertex_colors, Workspace ws, Dims d, const unsigned char* __restrict__ tile_flags,
+    int cs, int c0)   // cs: channels per pixel in the tensors, c0: first channel of the group this launch handles (width C)
 {
     constexpr int NS = C + 3;                  // scalars per pixel: C colour + (a,b,c)
     constexpr int N0 = (C == 1) ? 1 : 3;       // width of the first group
@@ -488,7 +489,7 @@ __global__ void __launch_bounds__(NW * 32, DIRT_BWD_MIN_BLOCKS * DIRT_BWD_WARPS 
     const float* verts = vertices + (size_t)b * d.V * 4;
     const int32_t* ids = face_ids + (size_t)b * H * W;
     float* gverts = grad_vertices + (size_t)b * d.V * 4;
-    float* gcols = grad_vertex_colors + (size_t)b * d.V * C;
+    float* gcols = grad_vertex_colors + (size_t)b * d.V * cs + c0;
     const size_t img = (size_t)b * H * W;
     const float halfW = 0.5f * (float)W, halfH = 0.5f * (float)H;
 
@@ -521,7 +522,7 @@ __global__ void __launch_bounds__(NW * 32, DIRT_BWD_MIN_BLOCKS * DIRT_BWD_WARPS 
                 if (col >= W || row >= H) continue;
                 const size_t p = img + (size_t)row * W + col;
 #pragma unroll
-                for (int ch = 0; ch < C; ++ch) grad_background[p * C + ch] = __ldg(grad_pixels + p * C + ch);
+                for (int ch = 0; ch < C; ++ch) grad_background[p * cs + c0 + ch] = __ldg(grad_pixels + p * cs + c0 + ch);
             }
         }
         continue;
@@ -550,7 +551,7 @@ __global__ void __launch_bounds__(NW * 32, DIRT_BWD_MIN_BLOCKS * DIRT_BWD_WARPS 
             if (C == 4) reinterpret_cast<float4*>(grad_background)[p] = __ldg(reinterpret_cast<const float4*>(grad_pixels) + p);
             else {
 #pragma unroll
-                for (int ch = 0; ch < C; ++ch) grad_background[p * C + ch] = __ldg(grad_pixels + p * C + ch);
+                for (int ch = 0; ch < C; ++ch) grad_background[p * cs + c0 + ch] = __ldg(grad_pixels + p * cs + c0 + ch);
             }
         }
         continue;
@@ -587,7 +588,7 @@ __global__ void __launch_bounds__(NW * 32, DIRT_BWD_MIN_BLOCKS * DIRT_BWD_WARPS 
             gp[pix][0] = v.x; gp[pix][1 % C] = v.y; gp[pix][2 % C] = v.z; gp[pix][3 % C] = v.w;
         } else {
 #pragma unroll
-            for (int ch = 0; ch < C; ++ch) gp[pix][ch] = __ldg(grad_pixels + p * C + ch);
+            for (int ch = 0; ch < C; ++ch) gp[pix][ch] = __ldg(grad_pixels + p * cs + c0 + ch);
         }
     }
 
@@ -607,7 +608,7 @@ __global__ void __launch_bounds__(NW * 32, DIRT_BWD_MIN_BLOCKS * DIRT_BWD_WARPS 
                 f < 0 ? make_float4(gp[pix][0], gp[pix][1 % C], gp[pix][2 % C], gp[pix][3 % C]) : make_float4(0.f, 0.f, 0.f, 0.f);
         } else {
 #pragma unroll
-            for (int ch = 0; ch < C; ++ch) grad_background[p * C + ch] = f < 0 ? gp[pix][ch] : 0.f;
+            for (int ch = 0; ch < C; ++ch) grad_background[p * cs + c0 + ch] = f < 0 ? gp[pix][ch] : 0.f;
         }
         // own coverage, or (interior pixels only) a covered 4-neighbour that could dilate into this pixel
         bool n = f >= 0;
@@ -626,7 +627,7 @@ __global__ void __launch_bounds__(NW * 32, DIRT_BWD_MIN_BLOCKS * DIRT_BWD_WARPS 
             const int hr = e / HALO_COLS, hc = e - hr * HALO_COLS;
             const int r = max(0, min(H - 1, trow0 - 1 + hr));
             const int c = max(0, min(W - 1, tcol0 - 1 + hc));
-            const float* src = pixels + (img + (size_t)r * W + c) * C;
+            const float* src = pixels + (img + (size_t)r * W + c) * (C == 4 ? 4 : cs) + (C == 4 ? 0 : c0);
             if (C == 4) cp_async_16(tile + e * 4, src);
             else {
 #pragma unroll
@@ -676,8 +677,8 @@ __global__ void __launch_bounds__(NW * 32, DIRT_BWD_MIN_BLOCKS * DIRT_BWD_WARPS 
             if (C == 4) scharr_smem_c4(tile, lrow0 + pix + 1, lcol + 1, sx, sy, sx1, sy1);
             else scharr_smem<C, N0>(tile, lrow0 + pix + 1, lcol + 1, sx, sy);
         } else {
-            scharr_global<C, N0>(pixels, b, row, col, d, 0, sx, sy);
-            if (TWO_GROUPS) scharr_global<C, 1>(pixels, b, row, col, d, 3, sx1, sy1);
+            scharr_global<C, N0>(pixels, b, row, col, d, c0, sx, sy);
+            if (TWO_GROUPS) scharr_global<C, 1>(pixels, b, row, col, d, c0 + 3, sx1, sy1);
         }
         int src0 = 0, code0 = 0;
         Fragment pos0 = me;
@@ -748,7 +749,7 @@ __global__ void __launch_bounds__(NW * 32, DIRT_BWD_MIN_BLOCKS * DIRT_BWD_WARPS 
         const int owner = owner_meta<C>(lane);
         // destination of this lane's finished sum: component (owner >> 2) & 3 of row `vid` of grad_vertices / grad_vertex_colors
         float* const owner_row = ((owner & 16) ? gverts : gcols) + ((owner >> 2) & 3);
-        const int owner_stride = (owner & 16) ? 4 : C;
+        const int owner_stride = (owner & 16) ? 4 : (C == 4 ? 4 : cs);
         const int kc0 = term[0].key_col, kc1 = term[1].key_col, kp0 = term[0].key_pos, kp1 = term[1].key_pos;
         unsigned direct = 0;   // bit 0/1: colour record of pixel 0/1, bit 2/3: position record of pixel 0/1
         int last = -1;
@@ -833,7 +834,7 @@ __global__ void __launch_bounds__(NW * 32, DIRT_BWD_MIN_BLOCKS * DIRT_BWD_WARPS 
                         if (C == 4) red_add_v4(gcols + (size_t)vid[k] * 4, w[k] * sc[pix][0], w[k] * sc[pix][1 % NS], w[k] * sc[pix][2 % NS], w[k] * sc[pix][3 % NS]);
                         else {
 #pragma unroll
-                            for (int j = 0; j < C; ++j) atomicAdd(gcols + (size_t)vid[k] * C + j, w[k] * sc[pix][j]);
+                            for (int j = 0; j < C; ++j) atomicAdd(gcols + (size_t)vid[k] * cs + j, w[k] * sc[pix][j]);
                         }
                     } else {
                         red_add_v4(gverts + (size_t)vid[k] * 4, w[k] * sc[pix][C], w[k] * sc[pix][C + 1], 0.f, w[k] * sc[pix][C + 2]);
@@ -859,36 +860,48 @@ cudaError_t launch_backward(const float* vertices, const float* pixels, const fl
     const long long total_tiles = (long long)d.B * d.btiles;
     if (total_tiles == 0) return cudaSuccess;
     ScopedKernelTimer timer(2, stream);
-    // fast path: the reference's default grouping of C in {1,3,4}; pointers vector-aligned where the kernel needs it
-    const bool default_groups = (d.C == 1 && groups.n == 1) || (d.C == 3 && groups.n == 1 && groups.width[0] == 3) ||
-                                (d.C == 4 && groups.n == 2 && groups.width[0] == 3 && groups.width[1] == 1);
-    const bool aligned4 = d.C != 4 || (((uintptr_t)pixels | (uintptr_t)grad_pixels | (uintptr_t)grad_background |
-                                        (uintptr_t)grad_vertex_colors) % 16 == 0);
-    const dim3 block(BWD_WARPS_PER_BLOCK * 32);
+    // C == 4 with the default grouping {3,1} and 16-byte aligned tensors: one fused launch.  Everything else: one launch
+    // per channel group (width 3 or 1) on its slice of the channels -- what the reference does at the Python level
+    // (dirt/rasterise_ops.py:86-108), except that nothing is sliced or copied and grad_vertices accumulates in place.
+    const bool fused4 = d.C == 4 && groups.n == 2 && groups.width[0] == 3 && groups.width[1] == 1 &&
+                        (((uintptr_t)pixels | (uintptr_t)grad_pixels | (uintptr_t)grad_background | (uintptr_t)grad_vertex_colors) % 16 == 0);
     const unsigned char* flags = tile_flags_valid ? ws.tile_flags : nullptr;
     auto grid_for = [&](int tiles_per_warp, int warps) {
         return dim3((unsigned)((d.btiles_x + warps * tiles_per_warp - 1) / (warps * tiles_per_warp)), (unsigned)d.btiles_y,
                     (unsigned)min(d.B, 65535));
     };
-    if (default_groups && aligned4 && d.C == 4)
+#ifdef DIRT_FORCE_GENERIC_BACKWARD   // the reference-shaped kernel (one atomic per term), kept for debugging
+    {
+        const unsigned grid = (unsigned)((total_tiles + BWD_WARPS_PER_BLOCK - 1) / BWD_WARPS_PER_BLOCK);
+        backward_generic_kernel<<<grid, BWD_WARPS_PER_BLOCK * 32, 0, stream>>>(vertices, pixels, grad_pixels, face_ids, grad_background,
+                                                                              grad_vertices, grad_vertex_colors, ws, d, groups);
+        ++*launches;
+        return cudaGetLastError();
+    }
+#endif
+    if (fused4) {
         backward_tile_kernel<4, BwdTiles<4>::value, BwdTiles<4>::warps>
             <<<grid_for(BwdTiles<4>::value, BwdTiles<4>::warps), BwdTiles<4>::warps * 32, 0, stream>>>(
-                vertices, pixels, grad_pixels, face_ids, grad_background, grad_vertices, grad_vertex_colors, ws, d, flags);
-    else if (default_groups && d.C == 3)
-        backward_tile_kernel<3, BwdTiles<3>::value, BwdTiles<3>::warps>
-            <<<grid_for(BwdTiles<3>::value, BwdTiles<3>::warps), BwdTiles<3>::warps * 32, 0, stream>>>(
-                vertices, pixels, grad_pixels, face_ids, grad_background, grad_vertices, grad_vertex_colors, ws, d, flags);
-    else if (default_groups && d.C == 1)
-        backward_tile_kernel<1, BwdTiles<1>::value, BwdTiles<1>::warps>
-            <<<grid_for(BwdTiles<1>::value, BwdTiles<1>::warps), BwdTiles<1>::warps * 32, 0, stream>>>(
-                vertices, pixels, grad_pixels, face_ids, grad_background, grad_vertices, grad_vertex_colors, ws, d, flags);
-    else {
-        const unsigned grid = (unsigned)((total_tiles + BWD_WARPS_PER_BLOCK - 1) / BWD_WARPS_PER_BLOCK);
-        backward_generic_kernel<<<grid, block, 0, stream>>>(vertices, pixels, grad_pixels, face_ids, grad_background,
-                                                            grad_vertices, grad_vertex_colors, ws, d, groups);
+                vertices, pixels, grad_pixels, face_ids, grad_background, grad_vertices, grad_vertex_colors, ws, d, flags, 4, 0);
+        ++*launches;
+        return cudaGetLastError();
     }
-    ++*launches;
-    return cudaGetLastError();
+    int c0 = 0;
+    for (int g = 0; g < groups.n; ++g) {
+        if (groups.width[g] == 3)
+            backward_tile_kernel<3, BwdTiles<3>::value, BwdTiles<3>::warps>
+                <<<grid_for(BwdTiles<3>::value, BwdTiles<3>::warps), BwdTiles<3>::warps * 32, 0, stream>>>(
+                    vertices, pixels, grad_pixels, face_ids, grad_background, grad_vertices, grad_vertex_colors, ws, d, flags, d.C, c0);
+        else
+            backward_tile_kernel<1, BwdTiles<1>::value, BwdTiles<1>::warps>
+                <<<grid_for(BwdTiles<1>::value, BwdTiles<1>::warps), BwdTiles<1>::warps * 32, 0, stream>>>(
+                    vertices, pixels, grad_pixels, face_ids, grad_background, grad_vertices, grad_vertex_colors, ws, d, flags, d.C, c0);
+        c0 += groups.width[g];
+        ++*launches;
+        const cudaError_t le = cudaGetLastError();
+        if (le != cudaSuccess) return le;
+    }
+    return cudaSuccess;
 }
 
 }  // namespace dirt
