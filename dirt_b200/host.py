@@ -72,10 +72,14 @@ class HostRasteriser:
         for s in (self.s_in, self.s_run, self.s_out):
             s.wait_stream(current)
         d = self.d
+        # geometry is small next to the images: it goes up in one piece, the per-chunk copies are the two image tensors
+        with torch.cuda.stream(self.s_in):
+            for k in ('vertices', 'vertex_colors', 'faces'):
+                d[k].copy_(host_in[k], non_blocking=True)
         for i, (b0, b1) in enumerate(self.bounds):
             n = b1 - b0
             with torch.cuda.stream(self.s_in):
-                for k in host_in:
+                for k in ('background', 'grad_pixels'):
                     d[k][b0:b1].copy_(host_in[k][b0:b1], non_blocking=True)
                 ev_in = torch.cuda.Event()
                 ev_in.record(self.s_in)
@@ -97,8 +101,11 @@ class HostRasteriser:
                 ev_run.record(self.s_run)
             with torch.cuda.stream(self.s_out):
                 self.s_out.wait_event(ev_run)
-                for k, t in self.h_out.items():
-                    t[b0:b1].copy_(d[k][b0:b1], non_blocking=True)
+                for k in ('pixels', 'grad_background'):
+                    self.h_out[k][b0:b1].copy_(d[k][b0:b1], non_blocking=True)
+        with torch.cuda.stream(self.s_out):   # after the last chunk's kernels (already awaited on this stream)
+            for k in ('grad_vertices', 'grad_vertex_colors'):
+                self.h_out[k].copy_(d[k], non_blocking=True)
         current.wait_stream(self.s_out)
         current.wait_stream(self.s_in)
         return self.h_out
