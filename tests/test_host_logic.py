@@ -98,3 +98,23 @@ def test_matrices_and_lighting_helpers():
     assert torch.allclose(flat[0], flat[1]) and torch.allclose(flat[1], flat[2])
     lit = lighting.diffuse_directional(torch.from_numpy(n), torch.ones(v.shape[0], 3), [1., 0., 0.], [1., 1., 1.])
     assert lit.shape == (v.shape[0], 3) and float(lit.min()) >= 0.
+
+
+def test_bench_reference_arm_prints_one_json_line():
+    """bench.py --impl reference runs the CPU port (no GPU needed) and must put exactly one JSON line on stdout,
+    with the keys the contract names."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    proc = subprocess.run([sys.executable, os.path.join(root, 'bench.py'), '--impl', 'reference', '--workload', 'cfg2',
+                           '--steps', '1', '--warmup', '0', '--cpu-sample', '1'],
+                          stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=300, check=True)
+    lines = [ln for ln in proc.stdout.decode().splitlines() if ln.strip()]
+    assert len(lines) == 1, lines
+    out = json.loads(lines[0])
+    assert out['impl'] == 'reference' and out['metric'] == 'fwd+bwd Mpixels/sec' and out['unit'] == 'Mpixels/s'
+    for key in ('value', 'n_gpus', 'steps', 'warmup', 'ms_per_step', 'higher_is_better', 'scaling', 'dtype', 'data', 'config',
+                'cpu_baseline', 'e2e'):
+        assert key in out, key
+    assert out['value'] > 0 and out['cpu_baseline']['kind'] == 'port' and out['e2e']['h2d_bytes_per_step'] == 0
