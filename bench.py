@@ -241,7 +241,7 @@ def cpu_baseline(scene, grad_pixels, sample_images, threads=None, min_seconds=10
         except AttributeError:
             threads = os.cpu_count() or 1
     n = min(sample_images, scene['background'].shape[0])
-    threads = max(1, min(threads, n))   # the oracle parallelises over images: idle OpenMP threads only steal SMT siblings
+    threads = max(1, threads)   # the oracle splits the work over images and, with fewer images than threads, bands of rows
     oracle.set_threads(threads)
     sub = {k: np.ascontiguousarray(v[:n]) for k, v in scene.items()}
     gp = np.ascontiguousarray(grad_pixels[:n])
@@ -428,7 +428,7 @@ def run_ours(args):
     if world == 1 and not args.no_cpu_baseline:
         mpix, n_img, reps, dt, threads = cpu_baseline(scene, prep.grad_pixels_host, args.cpu_sample)
         cpu = {'value': mpix, 'unit': UNIT, 'cores': threads, 'kind': 'port',
-               'sample': 'oracle/dirt_oracle.c (OpenMP over images) fwd+bwd on the first %d images of the workload, '
+               'sample': 'oracle/dirt_oracle.c (OpenMP over images x row bands) fwd+bwd on the first %d images of the workload, '
                          '%d passes in %.1f s' % (n_img, reps, dt)}
 
     out = {
@@ -473,7 +473,7 @@ def run_reference(args):
     gen, kwargs, desc = WORKLOADS[args.workload]
     kwargs = dict(kwargs)
     sample = min(args.cpu_sample, kwargs.get('batch', 1))
-    oracle.set_threads(max(1, min(host_threads, sample)))   # one image per thread is the port's parallel grain
+    oracle.set_threads(max(1, host_threads))   # work items are images x row bands: every host thread gets work
     kwargs['batch'] = sample if 'batch' in kwargs else None
     if kwargs.get('batch') is None:
         kwargs.pop('batch', None)
@@ -503,7 +503,7 @@ def run_reference(args):
         'config': {'workload': desc, 'name': args.workload, 'sample_images_per_step': B, 'height': H, 'width': W, 'channels': C,
                    'vertices': V, 'faces': F,
                    'note': 'the reference OpenGL/TensorFlow op cannot run in this image; this is the CPU port of its path '
-                           '(oracle/dirt_oracle.c, OpenMP over images) on a bounded sample of the same workload'},
+                           '(oracle/dirt_oracle.c, OpenMP over images x row bands, all host threads) on a bounded sample of the same workload'},
         'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': threads, 'kind': 'port',
                          'sample': '%d images of the workload per step, %d steps' % (B, args.steps)},
         'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},

@@ -312,26 +312,42 @@ static inline void tri_gbuffer(const Tri* t, int col, int row, float out[4])
     out[3] = cw;
 }
 
-/* visibility of one image: face_ids[H*W]; tris[F] filled on return */
-static void visibility_image(const float* verts, const int32_t* faces, int V, int F, int H, int W,
-                             Tri* tris, int32_t* face_ids, uint32_t* keys)
+/* visibility of rows [rb, re) of one image: face_ids / keys hold (re - rb) * W entries, row rb first; tris[F] filled on
+ * return.  (Work is split over images and, when there are fewer images than threads, over bands of rows: a band only
+ * needs the faces clipped to its rows, and the result per pixel does not depend on the split.) */
+static void visibility_rows(const float* verts, const int32_t* faces, int V, int F, int H, int W,
+                            Tri* tris, int32_t* face_ids, uint32_t* keys, int rb, int re)
 {
-    for (int i = 0; i < H * W; ++i) { face_ids[i] = -1; keys[i] = KEY_EMPTY; }
+    for (int i = 0; i < (re - rb) * W; ++i) { face_ids[i] = -1; keys[i] = KEY_EMPTY; }
     for (int f = 0; f < F; ++f) {
         Tri* t = &tris[f];
         setup_tri(verts, faces + (size_t)f * 3, V, H, W, t);
         if (t->kind == 0) continue;
-        for (int r = t->rmin; r <= t->rmax; ++r)
+        const int r0 = t->rmin > rb ? t->rmin : rb, r1 = t->rmax < re - 1 ? t->rmax : re - 1;
+        for (int r = r0; r <= r1; ++r)
             for (int c = t->cmin; c <= t->cmax; ++c) {
                 int in = (t->kind == 1) ? covers_normal(t, c, r) : covers_hard(t, c, r);
                 if (!in) continue;
                 uint32_t key = tri_depth_key(t, c, r);
-                if (key < keys[r * W + c]) { /* faces visited in ascending order: ties keep the earlier */
-                    keys[r * W + c] = key;
-                    face_ids[r * W + c] = f;
+                if (key < keys[(r - rb) * W + c]) { /* faces visited in ascending order: ties keep the earlier */
+                    keys[(r - rb) * W + c] = key;
+                    face_ids[(r - rb) * W + c] = f;
                 }
             }
     }
+}
+
+/* how many bands of rows each image is cut into so that B * bands work items keep every thread busy */
+static int bands_per_image(int B, int H)
+{
+    int threads = 1;
+#ifdef _OPENMP
+    threads = omp_get_max_threads();
+#endif
+    if (B <= 0 || B >= threads) return 1;
+    int nb = (threads + B - 1) / B;
+    if (nb > H) nb = H;
+    return nb < 1 ? 1 : nb;
 }
 
 /* the reference's own greedy split of C (rasterise_ops.py:80-108) */
@@ -375,19 +391,22 @@ int dirt_oracle_visibility(const float* vertices, const int32_t* faces, int32_t*
 {
     if (B < 0 || H <= 0 || W <= 0 || V < 0 || F < 0) return -1;
     int fail = 0;
+    const int NB = bands_per_image(B, H);
 #pragma omp parallel for schedule(dynamic, 1)
-    for (int b = 0; b < B; ++b) {
+    for (int item = 0; item < B * NB; ++item) {
+        const int b = item / NB, band = item % NB;
+        const int rb = (int)((long long)H * band / NB), re = (int)((long long)H * (band + 1) / NB);
         Tri* tris = (Tri*)malloc(sizeof(Tri) * (size_t)(F > 0 ? F : 1));
-        int32_t* ids = (int32_t*)malloc(sizeof(int32_t) * (size_t)H * W);
-        uint32_t* keys = (uint32_t*)malloc(sizeof(uint32_t) * (size_t)H * W);
+        int32_t* ids = (int32_t*)malloc(sizeof(int32_t) * (size_t)(re - rb) * W);
+        uint32_t* keys = (uint32_t*)malloc(sizeof(uint32_t) * (size_t)(re - rb) * W);
         if (!tris || !ids || !keys) { fail = 1; free(tris); free(ids); free(keys); continue; }
-        visibility_image(vertices + (size_t)b * V * 4, faces + (size_t)b * F * 3, V, F, H, W, tris, ids, keys);
-        if (face_ids) memcpy(face_ids + (size_t)b * H * W, ids, sizeof(int32_t) * (size_t)H * W);
+        visibility_rows(vertices + (size_t)b * V * 4, faces + (size_t)b * F * 3, V, F, H, W, tris, ids, keys, rb, re);
+        if (face_ids) memcpy(face_ids + ((size_t)b * H + rb) * W, ids, sizeof(int32_t) * (size_t)(re - rb) * W);
         if (gbuffer)
-            for (int r = 0; r < H; ++r)
+            for (int r = rb; r < re; ++r)
                 for (int c = 0; c < W; ++c) {
                     float* g = gbuffer + (((size_t)b * H + r) * W + c) * 4;
-                    int f = ids[r * W + c];
+                    int f = ids[(r - rb) * W + c];
                     if (f < 0) { g[0] = g[1] = g[2] = -1.0f; g[3] = INFINITY; }
                     else tri_gbuffer(&tris[f], c, r, g);
                 }
@@ -402,18 +421,21 @@ int dirt_oracle_forward(const float* background, const float* vertices, const fl
 {
     if (B < 0 || H <= 0 || W <= 0 || C <= 0 || V < 0 || F < 0) return -1;
     int fail = 0;
+    const int NB = bands_per_image(B, H);
 #pragma omp parallel for schedule(dynamic, 1)
-    for (int b = 0; b < B; ++b) {
+    for (int item = 0; item < B * NB; ++item) {
+        const int b = item / NB, band = item % NB;
+        const int rb = (int)((long long)H * band / NB), re = (int)((long long)H * (band + 1) / NB);
         Tri* tris = (Tri*)malloc(sizeof(Tri) * (size_t)(F > 0 ? F : 1));
-        int32_t* ids = (int32_t*)malloc(sizeof(int32_t) * (size_t)H * W);
-        uint32_t* keys = (uint32_t*)malloc(sizeof(uint32_t) * (size_t)H * W);
+        int32_t* ids = (int32_t*)malloc(sizeof(int32_t) * (size_t)(re - rb) * W);
+        uint32_t* keys = (uint32_t*)malloc(sizeof(uint32_t) * (size_t)(re - rb) * W);
         if (!tris || !ids || !keys) { fail = 1; free(tris); free(ids); free(keys); continue; }
-        visibility_image(vertices + (size_t)b * V * 4, faces + (size_t)b * F * 3, V, F, H, W, tris, ids, keys);
+        visibility_rows(vertices + (size_t)b * V * 4, faces + (size_t)b * F * 3, V, F, H, W, tris, ids, keys, rb, re);
         const float* cols = vertex_colors + (size_t)b * V * C;
-        for (int r = 0; r < H; ++r)
+        for (int r = rb; r < re; ++r)
             for (int c = 0; c < W; ++c) {
                 size_t pix = ((size_t)b * H + r) * W + c;
-                int f = ids[r * W + c];
+                int f = ids[(r - rb) * W + c];
                 if (f < 0) {
                     for (int ch = 0; ch < C; ++ch) pixels[pix * C + ch] = background[pix * C + ch];
                 } else {
@@ -430,7 +452,7 @@ int dirt_oracle_forward(const float* background, const float* vertices, const fl
                     }
                 }
             }
-        if (face_ids_out) memcpy(face_ids_out + (size_t)b * H * W, ids, sizeof(int32_t) * (size_t)H * W);
+        if (face_ids_out) memcpy(face_ids_out + ((size_t)b * H + rb) * W, ids, sizeof(int32_t) * (size_t)(re - rb) * W);
         free(tris); free(ids); free(keys);
     }
     return fail ? -2 : 0;
@@ -474,11 +496,13 @@ static inline float scharr_comp(float nn, float np, float pn, float pp, float mn
     return fmaf(Y, 0.3125f, X * 0.09375f);
 }
 
-static void backward_image_group(const float* verts, const Tri* tris, const int32_t* ids,
+static void backward_image_group(const float* verts, const Tri* tris, const int32_t* ids_rows, int rb,
                                  const float* pixels, const float* grad_pixels,
-                                 double* gverts /*[V,4]*/, int b, int B, int H, int W, int C, int c0, int n)
+                                 double* gverts /*[V,4]*/, int b, int B, int H, int W, int C, int c0, int n, int r0, int r1)
 {
-    for (int r = 0; r < H; ++r)
+    /* rows [r0, r1) of the image; ids_rows holds the visibility buffer from row rb on (rb <= r0 - 1 unless r0 == 0) */
+#define IDS(r_, c_) ids_rows[((r_) - rb) * W + (c_)]
+    for (int r = r0; r < r1; ++r)
         for (int c = 0; c < W; ++c) {
             /* at(ox,oy) is image (row r - oy, col c + ox) */
 #define AT(ox, oy) group_at(pixels, b, r - (oy), c + (ox), B, H, W, C, c0, n)
@@ -495,7 +519,7 @@ static void backward_image_group(const float* verts, const Tri* tris, const int3
             sy[1] = scharr_comp(a_mm.y, a_pm.y, a_mp.y, a_pp.y, a_0m.y, a_0p.y);
             sy[2] = scharr_comp(a_mm.z, a_pm.z, a_mp.z, a_pp.z, a_0m.z, a_0p.z);
 
-            int f = ids[r * W + c];
+            int f = IDS(r, c);
             float g[4] = {-1.0f, -1.0f, -1.0f, INFINITY};
             if (f >= 0) tri_gbuffer(&tris[f], c, r, g);
 
@@ -507,7 +531,7 @@ static void backward_image_group(const float* verts, const Tri* tris, const int3
                 if ((c + r) % 2 == 1) { dx = -dx; dy = -dy; }
                 for (int attempt = 0; attempt < 2; ++attempt) {
                     int nc = c + dx, nr = r - dy; /* buffer_y + dy is image row r - dy */
-                    int fn = ids[nr * W + nc];
+                    int fn = IDS(nr, nc);
                     if (fn >= 0) {
                         const Tri* tn = &tris[fn];
                         int differs = (f < 0) || tn->v[0] != tris[f].v[0] || tn->v[1] != tris[f].v[1] ||
@@ -549,6 +573,7 @@ static void backward_image_group(const float* verts, const Tri* tris, const int3
                 }
             }
         }
+#undef IDS
 }
 
 int dirt_oracle_backward(const float* vertices, const int32_t* faces, const float* pixels,
@@ -573,24 +598,34 @@ int dirt_oracle_backward(const float* vertices, const int32_t* faces, const floa
         ng = default_groups(C, groups);
     }
     int fail = 0;
+    /* work items: (image, band of rows); every item sums into its own double accumulators, which are added up per image
+     * in band order afterwards (deterministic for a given thread count) */
+    const int NB = bands_per_image(B, H);
+    const size_t nv = (size_t)(V > 0 ? V : 1);
+    double* gv_all = (double*)calloc((size_t)(B > 0 ? B : 1) * NB * nv * 4, sizeof(double));
+    double* gc_all = (double*)calloc((size_t)(B > 0 ? B : 1) * NB * nv * C, sizeof(double));
+    if (!gv_all || !gc_all) { free(gv_all); free(gc_all); free(groups); return -2; }
 #pragma omp parallel for schedule(dynamic, 1)
-    for (int b = 0; b < B; ++b) {
+    for (int item = 0; item < B * NB; ++item) {
+        const int b = item / NB, band = item % NB;
+        const int r0 = (int)((long long)H * band / NB), r1 = (int)((long long)H * (band + 1) / NB);
+        const int rb = r0 > 0 ? r0 - 1 : 0, re = r1 < H ? r1 + 1 : H;   /* the dilation looks one row up and down */
         Tri* tris = (Tri*)malloc(sizeof(Tri) * (size_t)(F > 0 ? F : 1));
-        int32_t* ids = (int32_t*)malloc(sizeof(int32_t) * (size_t)H * W);
-        uint32_t* keys = (uint32_t*)malloc(sizeof(uint32_t) * (size_t)H * W);
-        double* gv = (double*)calloc((size_t)(V > 0 ? V : 1) * 4, sizeof(double));
-        double* gc = (double*)calloc((size_t)(V > 0 ? V : 1) * C, sizeof(double));
-        if (!tris || !ids || !keys || !gv || !gc) {
-            fail = 1; free(tris); free(ids); free(keys); free(gv); free(gc);
+        int32_t* ids = (int32_t*)malloc(sizeof(int32_t) * (size_t)(re - rb) * W);
+        uint32_t* keys = (uint32_t*)malloc(sizeof(uint32_t) * (size_t)(re - rb) * W);
+        if (!tris || !ids || !keys) {
+            fail = 1; free(tris); free(ids); free(keys);
             continue;
         }
+        double* gv = gv_all + (size_t)item * nv * 4;
+        double* gc = gc_all + (size_t)item * nv * C;
         const float* verts = vertices + (size_t)b * V * 4;
-        visibility_image(verts, faces + (size_t)b * F * 3, V, F, H, W, tris, ids, keys);
+        visibility_rows(verts, faces + (size_t)b * F * 3, V, F, H, W, tris, ids, keys, rb, re);
         /* colour gradients and background gradient (:135-148): undilated barycentrics, all channels */
-        for (int r = 0; r < H; ++r)
+        for (int r = r0; r < r1; ++r)
             for (int c = 0; c < W; ++c) {
                 size_t pix = ((size_t)b * H + r) * W + c;
-                int f = ids[r * W + c];
+                int f = ids[(r - rb) * W + c];
                 if (f >= 0) {
                     float g[4];
                     tri_gbuffer(&tris[f], c, r, g);
@@ -604,13 +639,25 @@ int dirt_oracle_backward(const float* vertices, const int32_t* faces, const floa
             }
         int c0 = 0;
         for (int gi = 0; gi < ng; ++gi) {
-            backward_image_group(verts, tris, ids, pixels, grad_pixels, gv, b, B, H, W, C, c0, groups[gi]);
+            backward_image_group(verts, tris, ids, rb, pixels, grad_pixels, gv, b, B, H, W, C, c0, groups[gi], r0, r1);
             c0 += groups[gi];
         }
-        for (size_t i = 0; i < (size_t)V * 4; ++i) grad_vertices[(size_t)b * V * 4 + i] = (float)gv[i];
-        for (size_t i = 0; i < (size_t)V * C; ++i) grad_vertex_colors[(size_t)b * V * C + i] = (float)gc[i];
-        free(tris); free(ids); free(keys); free(gv); free(gc);
+        free(tris); free(ids); free(keys);
     }
+#pragma omp parallel for schedule(static)
+    for (int b = 0; b < B; ++b) {
+        for (size_t i = 0; i < (size_t)V * 4; ++i) {
+            double acc = 0.0;
+            for (int band = 0; band < NB; ++band) acc += gv_all[((size_t)b * NB + band) * nv * 4 + i];
+            grad_vertices[(size_t)b * V * 4 + i] = (float)acc;
+        }
+        for (size_t i = 0; i < (size_t)V * C; ++i) {
+            double acc = 0.0;
+            for (int band = 0; band < NB; ++band) acc += gc_all[((size_t)b * NB + band) * nv * C + i];
+            grad_vertex_colors[(size_t)b * V * C + i] = (float)acc;
+        }
+    }
+    free(gv_all); free(gc_all);
     free(groups);
     return fail ? -2 : 0;
 }

@@ -217,3 +217,30 @@ def test_random_planar_triangulations_are_covered_exactly_once(oracle):
             np.testing.assert_allclose(gbuf[0][..., 3][cov], 1.0, rtol=1e-6)
 
     check()
+
+
+@pytest.mark.parametrize('threads', [1, 3, 64, 500])
+def test_results_do_not_depend_on_the_thread_count(oracle, threads):
+    """The oracle splits its work over images and, with fewer images than threads, over bands of rows (so that the CPU
+    baseline uses every host thread).  Visibility, pixels and grad_background must be identical for every split; the
+    vertex gradients are double-precision sums added up in a different grouping, rounded to fp32 once."""
+    from dirt_b200 import scenes
+    s = scenes.random_soup(batch=2, channels=4, seed=11)
+    gp = None
+    results = []
+    before = oracle.threads()
+    try:
+        for t in (1, threads):
+            oracle.set_threads(t)
+            px, ids = oracle.forward(**s, return_face_ids=True)
+            if gp is None:
+                gp = np.random.default_rng(5).standard_normal(px.shape).astype(np.float32)
+            results.append((px, ids) + tuple(oracle.backward(s['vertices'], s['faces'], px, gp)))
+    finally:
+        oracle.set_threads(before)
+    (px0, ids0, gb0, gv0, gc0), (px1, ids1, gb1, gv1, gc1) = results
+    np.testing.assert_array_equal(ids1, ids0)
+    np.testing.assert_array_equal(px1, px0)
+    np.testing.assert_array_equal(gb1, gb0)
+    np.testing.assert_allclose(gv1, gv0, rtol=1e-6, atol=1e-6 * np.abs(gv0).max())
+    np.testing.assert_allclose(gc1, gc0, rtol=1e-6, atol=1e-6 * np.abs(gc0).max())
