@@ -74,7 +74,9 @@ def specular_directional(vertex_positions, vertex_normals, vertex_reflectivities
     camera_position = torch.as_tensor(camera_position, dtype=torch.float32, device=dev)
     shininess = torch.as_tensor(shininess, dtype=torch.float32, device=dev)
     to_light = -light_direction
-    reflected = -to_light + 2. * torch.matmul(vertex_normals, to_light[..., None]) * vertex_normals
+    # (the reference adds `-to_light` of shape [*,3] to a [*,V,3] tensor, which only broadcasts without batch dimensions,
+    # dirt/lighting.py:272; the vertex axis is inserted here so that batches work as its docstring promises)
+    reflected = -to_light[..., None, :] + 2. * torch.matmul(vertex_normals, to_light[..., None]) * vertex_normals
     to_camera = camera_position[..., None, :] - vertex_positions
     # the reference adds its epsilon after the division (dirt/lighting.py:279); kept for parity
     cosines = ((to_camera / torch.linalg.norm(to_camera, dim=-1, keepdim=True) + 1.e-12) * reflected).sum(-1, keepdim=True)

@@ -1,0 +1,196 @@
+"""CPU tests of the helpers on either side of the hot path: dirt_b200.matrices / lighting /
+projection against independent restatements of the reference formulas (plain numpy loops on small cases, scipy for the
+rotation), each citing the reference lines it follows.  The reference package itself needs TensorFlow 1.x and cannot be
+imported here."""
+import numpy as np
+import pytest
+import torch
+
+from dirt_b200 import lighting, matrices, projection, scenes
+
+
+def _rng(seed):
+    return np.random.default_rng(seed)
+
+
+# ---- matrices (dirt/matrices.py) ------------------------------------------------------------------------------------
+
+def test_rodrigues_matches_the_reference_layout():
+    """dirt/matrices.py:15-61: Rodrigues' formula with K laid out exactly as the reference writes it (:43-48, "follows the
+    OpenCV docs' definition"): the result equals the usual column-vector rotation matrix element for element, so used on
+    row vectors (`v @ R`, the module's convention) it turns them by MINUS the angle.  Batched, 4x4 by default."""
+    from scipy.spatial.transform import Rotation
+    vecs = _rng(0).standard_normal((5, 7, 3)).astype(np.float32)
+    ours = matrices.rodrigues(torch.from_numpy(vecs)).numpy()
+    assert ours.shape == (5, 7, 4, 4)
+    want = Rotation.from_rotvec(vecs.reshape(-1, 3).astype(np.float64)).as_matrix().reshape(5, 7, 3, 3)
+    np.testing.assert_allclose(ours[..., :3, :3], want, atol=2e-6)
+    np.testing.assert_array_equal(ours[..., 3, :], np.broadcast_to([0., 0., 0., 1.], (5, 7, 4)))
+    np.testing.assert_array_equal(ours[..., :3, 3], np.zeros((5, 7, 3)))
+    np.testing.assert_allclose(matrices.rodrigues(torch.from_numpy(vecs), three_by_three=True).numpy(), ours[..., :3, :3])
+    # the literal K of the reference for one vector (:43-47), indexed [in][out]
+    x, y, z = 0.3, -0.5, 0.8
+    n = np.sqrt(x * x + y * y + z * z)
+    a = np.array([x, y, z]) / n
+    K = np.array([[0., -a[2], a[1]], [a[2], 0., -a[0]], [-a[1], a[0], 0.]])
+    lit = np.cos(n) * np.eye(3) + (1 - np.cos(n)) * np.outer(a, a) + np.sin(n) * K
+    np.testing.assert_allclose(matrices.rodrigues([x, y, z], three_by_three=True).numpy(), lit, atol=1e-6)
+    # the zero vector is the identity and differentiable (the reference adds 1e-12 for that, :36-38)
+    z = torch.zeros(3, requires_grad=True)
+    r = matrices.rodrigues(z)
+    np.testing.assert_allclose(r.detach().numpy(), np.eye(4), atol=1e-6)
+    r.sum().backward()
+    assert torch.isfinite(z.grad).all()
+
+
+def test_translation_scale_compose_act_on_row_vectors():
+    """dirt/matrices.py:64-107,183-207: points are rows, `compose(a, b)` applies a first."""
+    p = np.array([[1., 2., 3., 1.]], np.float32)
+    t = matrices.translation([10., 20., 30.]).numpy()
+    s = matrices.scale([2., 3., 4.]).numpy()
+    np.testing.assert_allclose(p @ t, [[11., 22., 33., 1.]])
+    np.testing.assert_allclose(p @ s, [[2., 6., 12., 1.]])
+    np.testing.assert_allclose(p @ matrices.compose(t, s).numpy(), (p @ t) @ s)
+    np.testing.assert_allclose(p @ matrices.compose(s, t).numpy(), (p @ s) @ t)
+    batch = matrices.translation(torch.from_numpy(_rng(1).standard_normal((4, 3)).astype(np.float32)))
+    assert batch.shape == (4, 4, 4)
+    np.testing.assert_allclose(matrices.pad_3x3_to_4x4(np.eye(3, dtype=np.float32) * 2.).numpy(), np.diag([2., 2., 2., 1.]))
+
+
+def test_perspective_projection_maps_the_frustum_to_the_ndc_cube():
+    """dirt/matrices.py:110-153: OpenGL convention, camera looks along -z, `aspect` = height / width."""
+    near, far, right, aspect = 0.5, 40., 0.25, 0.75
+    m = matrices.perspective_projection(near, far, right, aspect).numpy()
+    top = right * aspect
+
+    def ndc(p):
+        c = np.array(list(p) + [1.], np.float64) @ m.astype(np.float64)
+        return c[:3] / c[3]
+
+    np.testing.assert_allclose(ndc([right, top, -near]), [1., 1., -1.], atol=1e-6)
+    np.testing.assert_allclose(ndc([-right, -top, -near]), [-1., -1., -1.], atol=1e-6)
+    np.testing.assert_allclose(ndc([0., 0., -far]), [0., 0., 1.], atol=1e-5)
+    s = far / near
+    np.testing.assert_allclose(ndc([right * s, top * s, -far]), [1., 1., 1.], atol=1e-5)
+    # clip-space w is the view-space distance along the viewing direction
+    assert (np.array([0.3, -0.2, -7., 1.]) @ m)[3] == pytest.approx(7.)
+    np.testing.assert_allclose(m, scenes.perspective_projection(near, far, right, aspect), atol=1e-7)
+    assert matrices.perspective_projection(torch.tensor([0.1, 0.2]), 20., 0.1, 1.).shape == (2, 4, 4)
+
+
+# ---- lighting (dirt/lighting.py) ------------------------------------------------------------------------------------
+
+def _face_normal(v, f):
+    n = np.cross(v[f[1]] - v[f[0]], v[f[2]] - v[f[0]])
+    return n / (np.linalg.norm(n) + 1.e-12)
+
+
+def _vertex_normals_loops(v, faces):
+    """dirt/lighting.py:24-31,34-93: every face adds its UNIT normal to its three vertices; the sum is renormalised."""
+    out = np.zeros((v.shape[0], 3))
+    for f in faces:
+        n = _face_normal(v[:, :3].astype(np.float64), f)
+        for k in range(3):
+            out[f[k]] += n
+    return out / (np.linalg.norm(out, axis=-1, keepdims=True) + 1.e-12)
+
+
+@pytest.mark.parametrize('with_w', [False, True])
+def test_vertex_normals_match_the_loop_restatement(with_w):
+    v, f = scenes.icosphere(1)
+    r = _rng(2)
+    v = (v * (1. + 0.3 * r.standard_normal((v.shape[0], 1)))).astype(np.float32)   # not a sphere any more
+    if with_w:
+        v = np.concatenate([v, np.ones((v.shape[0], 1), np.float32)], axis=1)      # the w coordinate is dropped (:59)
+    got = lighting.vertex_normals(torch.from_numpy(v), torch.from_numpy(f)).numpy()
+    np.testing.assert_allclose(got, _vertex_normals_loops(v, f), atol=2e-6)
+    np.testing.assert_allclose(np.linalg.norm(got, axis=-1), 1., atol=1e-5)
+    # batched meshes with common topology (:37-38)
+    vb = np.stack([v, v[:, ::-1].copy() if not with_w else v * 1.5])
+    gb = lighting.vertex_normals(torch.from_numpy(vb), torch.from_numpy(f)).numpy()
+    for i in range(2):
+        np.testing.assert_allclose(gb[i], _vertex_normals_loops(vb[i], f), atol=2e-6)
+
+
+def test_split_vertices_and_pre_split_normals():
+    """dirt/lighting.py:101-179: after splitting, every vertex belongs to one face and carries that face's unit normal."""
+    v, f = scenes.cube()
+    sv, sf = lighting.split_vertices_by_face(torch.from_numpy(v), torch.from_numpy(f))
+    assert sv.shape == (f.shape[0] * 3, 3) and sf.dtype == torch.int32
+    np.testing.assert_array_equal(sf.numpy(), np.arange(f.shape[0] * 3).reshape(-1, 3))
+    np.testing.assert_array_equal(sv.numpy(), v[f.reshape(-1)])
+    n = lighting.vertex_normals_pre_split(sv, sf).numpy()
+    for i, face in enumerate(f):
+        want = _face_normal(v.astype(np.float64), face)
+        for k in range(3):
+            np.testing.assert_allclose(n[3 * i + k], want, atol=1e-6)
+    # the general routine gives the same answer on a split mesh
+    np.testing.assert_allclose(lighting.vertex_normals(sv, sf).numpy(), n, atol=1e-6)
+
+
+@pytest.mark.parametrize('double_sided', [True, False])
+def test_reflectance_models_match_the_loop_restatements(double_sided):
+    """dirt/lighting.py:182-225 (Lambert, directional), :228-288 (Phong, directional; the epsilon is added AFTER the
+    normalising division, :279), :291-343 (Lambert, point light)."""
+    r = _rng(3)
+    V, C = 9, 3
+    pos = r.standard_normal((2, V, 3)).astype(np.float32)
+    nrm = r.standard_normal((2, V, 3)).astype(np.float32)
+    nrm /= np.linalg.norm(nrm, axis=-1, keepdims=True)
+    col = r.uniform(size=(2, V, C)).astype(np.float32)
+    ldir = r.standard_normal((2, 3)).astype(np.float32)
+    ldir /= np.linalg.norm(ldir, axis=-1, keepdims=True)
+    lcol = r.uniform(size=(2, C)).astype(np.float32)
+    lpos = r.standard_normal((2, 3)).astype(np.float32) * 3.
+    cam = r.standard_normal((2, 3)).astype(np.float32) * 4.
+    shin = np.array([3., 8.], np.float32)
+    side = (lambda c: abs(c)) if double_sided else (lambda c: max(c, 0.))
+
+    want_dd = np.zeros((2, V, C)); want_sp = np.zeros((2, V, C)); want_dp = np.zeros((2, V, C))
+    for b in range(2):
+        for i in range(V):
+            n, p = nrm[b, i].astype(np.float64), pos[b, i].astype(np.float64)
+            want_dd[b, i] = lcol[b] * col[b, i] * side(float(n @ -ldir[b]))
+            to_light = -ldir[b].astype(np.float64)
+            reflected = -to_light + 2. * (n @ to_light) * n
+            to_cam = cam[b] - p
+            want_sp[b, i] = lcol[b] * col[b, i] * side(float((to_cam / np.linalg.norm(to_cam) + 1.e-12) @ reflected)) ** shin[b]
+            rel = p - lpos[b]
+            want_dp[b, i] = lcol[b] * col[b, i] * side(float(n @ (rel / (np.linalg.norm(rel) + 1.e-12))))
+    t = torch.from_numpy
+    np.testing.assert_allclose(lighting.diffuse_directional(t(nrm), t(col), t(ldir), t(lcol), double_sided).numpy(), want_dd, atol=2e-6)
+    np.testing.assert_allclose(lighting.specular_directional(t(pos), t(nrm), t(col), t(ldir), t(lcol), t(cam), t(shin), double_sided).numpy(),
+                               want_sp, rtol=2e-4, atol=2e-6)
+    np.testing.assert_allclose(lighting.diffuse_point(t(pos), t(nrm), t(col), t(lpos), t(lcol), double_sided).numpy(), want_dp, atol=2e-6)
+
+
+# ---- projection (dirt/projection.py) --------------------------------------------------------------------------------
+
+def test_unprojected_rays_pass_through_the_points_that_project_to_the_pixels():
+    """dirt/projection.py:6-70: pixel (x, y) with y down -> NDC with y up; ray start on the near plane, delta towards the
+    z_ndc = 0 surface.  A world point must lie on the ray of the pixel it projects to."""
+    W, H = 64, 48
+    view = matrices.compose(matrices.rodrigues([0.1, -0.4, 0.05]), matrices.translation([0.2, -0.1, -5.]))
+    proj = matrices.perspective_projection(0.1, 30., 0.08, H / W)
+    world_to_clip = matrices.compose(view, proj).numpy().astype(np.float64)
+    clip_to_world = np.linalg.inv(world_to_clip)
+    pts = _rng(4).uniform(-1., 1., size=(11, 3))
+    clip = np.concatenate([pts, np.ones((11, 1))], axis=1) @ world_to_clip
+    ndc = clip[:, :3] / clip[:, 3:]
+    assert (np.abs(ndc) < 1.).all()
+    pix = np.stack([(ndc[:, 0] + 1.) * 0.5 * W, (1. - ndc[:, 1]) * 0.5 * H], axis=1)   # y down, as rasterise lays rows out
+    starts, deltas = projection.unproject_pixels_to_rays(pix.astype(np.float32), clip_to_world.astype(np.float32), [W, H])
+    starts, deltas = starts.numpy().astype(np.float64), deltas.numpy().astype(np.float64)
+    for i in range(11):
+        d = deltas[i] / np.linalg.norm(deltas[i])
+        off = pts[i] - starts[i]
+        assert np.linalg.norm(off - (off @ d) * d) < 2e-3          # the point is on the ray
+        assert off @ d > 0                                           # in front of the near plane
+    # ray starts are on the near plane: they project to z_ndc = -1
+    sc = np.concatenate([starts, np.ones((11, 1))], axis=1) @ world_to_clip
+    np.testing.assert_allclose(sc[:, 2] / sc[:, 3], -1., atol=2e-3)
+    # leading image dimensions (A*) with their own matrices and sizes, trailing pixel dimensions (B*)
+    s2, d2 = projection.unproject_pixels_to_rays(np.tile(pix.astype(np.float32)[None, None], (2, 3, 1, 1)).reshape(2, 3, 11, 2),
+                                                 np.tile(clip_to_world.astype(np.float32)[None], (2, 1, 1)), [[W, H], [W, H]])
+    assert s2.shape == (2, 3, 11, 3) and d2.shape == (2, 3, 11, 3)
+    np.testing.assert_allclose(s2[1, 2].numpy(), starts, atol=1e-4)
