@@ -194,3 +194,59 @@ def test_unprojected_rays_pass_through_the_points_that_project_to_the_pixels():
                                                  np.tile(clip_to_world.astype(np.float32)[None], (2, 1, 1)), [[W, H], [W, H]])
     assert s2.shape == (2, 3, 11, 3) and d2.shape == (2, 3, 11, 3)
     np.testing.assert_allclose(s2[1, 2].numpy(), starts, atol=1e-4)
+
+
+# ---- texture lookup of examples/textured.py (samples/textured.py:15-60) ----------------------------------------------
+
+def _load_textured_example():
+    import importlib.util
+    import os
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'examples', 'textured.py')
+    spec = importlib.util.spec_from_file_location('textured_example', path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def test_texture_lookup_of_the_textured_example():
+    ex = _load_textured_example()
+    r = _rng(6)
+    tex = r.uniform(size=(5, 7, 3)).astype(np.float32)
+    uv = r.uniform(-1.5, 2.5, size=(4, 6, 2)).astype(np.float32)
+    idx = ex.uvs_to_pixel_indices(torch.from_numpy(uv), tex.shape[:2]).numpy()
+    # (u, v) -> (row, column) = (v mod 1 * H, u mod 1 * W): u = v = 0 is the top-left corner
+    np.testing.assert_allclose(idx[..., 0], (uv[..., 1] % 1.) * 5, atol=1e-5)
+    np.testing.assert_allclose(idx[..., 1], (uv[..., 0] % 1.) * 7, atol=1e-5)
+    clamped = ex.uvs_to_pixel_indices(torch.from_numpy(uv), tex.shape[:2], mode='clamp').numpy()
+    np.testing.assert_allclose(clamped[..., 0], np.clip(uv[..., 1], 0, 1) * 5, atol=1e-5)
+    got = ex.sample_texture(torch.from_numpy(tex), torch.from_numpy(idx)).numpy()
+    want = np.zeros(idx.shape[:-1] + (3,))
+    for i in np.ndindex(idx.shape[:-1]):
+        rr, cc = idx[i]
+        r0, c0 = int(np.floor(rr)), int(np.floor(cc))
+        fr, fc = rr - r0, cc - c0
+        t = lambda a, b: tex[a % 5, b % 7].astype(np.float64)
+        want[i] = t(r0, c0) * (1 - fc) * (1 - fr) + t(r0, c0 + 1) * fc * (1 - fr) + t(r0 + 1, c0) * (1 - fc) * fr + t(r0 + 1, c0 + 1) * fc * fr
+    np.testing.assert_allclose(got, want, atol=1e-5)
+    # integer indices return the texel itself; the lookup is differentiable w.r.t. the texture
+    np.testing.assert_allclose(ex.sample_texture(torch.from_numpy(tex), torch.tensor([[2., 3.]])).numpy()[0], tex[2, 3], atol=1e-6)
+    t_param = torch.from_numpy(tex).requires_grad_(True)
+    ex.sample_texture(t_param, torch.from_numpy(idx)).sum().backward()
+    assert float(t_param.grad.sum()) == pytest.approx(idx[..., 0].size * 3, rel=1e-4)   # bilinear weights sum to one
+
+
+def test_shader_of_the_textured_example_on_a_synthetic_gbuffer():
+    ex = _load_textured_example()
+    tex = ex.checker_texture(size=32, squares=4)
+    assert tex.shape == (32, 32, 3) and float(tex.min()) >= 0. and float(tex.max()) <= 1.
+    g = torch.zeros(4, 5, 6)
+    g[1:3, 1:4, 0] = 1.                                    # covered block
+    g[..., 1:3] = torch.rand(4, 5, 2, generator=torch.Generator().manual_seed(0))
+    g[..., 3:] = torch.tensor([0., 0., 1.])
+    out = ex.shader_fn(g, tex, torch.tensor([0., 0., -1.]))
+    assert out.shape == (4, 5, 3)
+    np.testing.assert_allclose(out[0, 0].numpy(), [0., 0., 0.3], atol=1e-6)              # background colour where mask = 0
+    unlit = ex.sample_texture(tex, ex.uvs_to_pixel_indices(g[..., 1:3], tex.shape[:2]))
+    np.testing.assert_allclose(out[1, 1].numpy(), (unlit[1, 1] * (0.4 + 0.6)).numpy(), atol=1e-5)   # normal faces the light
+    verts, uvs, faces = ex.build_cube()
+    assert len(verts) == 24 and len(uvs) == 24 and len(faces) == 12
