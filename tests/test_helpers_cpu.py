@@ -250,3 +250,36 @@ def test_shader_of_the_textured_example_on_a_synthetic_gbuffer():
     np.testing.assert_allclose(out[1, 1].numpy(), (unlit[1, 1] * (0.4 + 0.6)).numpy(), atol=1e-5)   # normal faces the light
     verts, uvs, faces = ex.build_cube()
     assert len(verts) == 24 and len(uvs) == 24 and len(faces) == 12
+
+
+def test_deferred_example_shades_an_oracle_gbuffer():
+    """examples/deferred.py (samples/deferred.py): the scene and the per-pixel shader, with the CPU oracle standing in
+    for the rasteriser; the shaded image must equal shading evaluated pixel by pixel from the formulas."""
+    import importlib.util
+    import os
+    from oracle import oracle
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'examples', 'deferred.py')
+    spec = importlib.util.spec_from_file_location('deferred_example', path)
+    ex = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ex)
+    ex.frame_width, ex.frame_height = 80, 60
+    vo, vc, attrs, faces, view = ex.scene(torch.device('cpu'))
+    assert vc.shape == (36, 4) and attrs.shape == (36, 10) and faces.shape == (12, 3)
+    g = oracle.forward(np.zeros((1, 60, 80, 10), np.float32), vc.detach().numpy()[None], attrs.detach().numpy()[None], faces.numpy()[None])[0]
+    light = torch.nn.functional.normalize(torch.tensor([1., -0.3, -0.5]), dim=0)
+    img = ex.shader_fn(torch.from_numpy(g), view, light).numpy()
+    assert img.shape == (60, 80, 3) and img.min() >= 0. and img.max() <= 1.
+    covered = g[..., 0] > 0.5
+    assert 0.05 < covered.mean() < 0.6
+    np.testing.assert_allclose(img[~covered], np.broadcast_to([0., 0., 0.3], img[~covered].shape), atol=1e-6)
+    cam = np.linalg.inv(view.numpy().astype(np.float64))[3, :3]
+    l = light.numpy().astype(np.float64)
+    rows, cols = np.nonzero(covered)
+    for r, c in list(zip(rows, cols))[::37]:
+        m, p, a, n = g[r, c, 0], g[r, c, 1:4].astype(np.float64), g[r, c, 4:7].astype(np.float64), g[r, c, 7:].astype(np.float64)
+        diffuse = np.array([1., 0., 0.]) * a * max(float(n @ -l), 0.)
+        refl = l + 2. * (n @ -l) * n
+        to_cam = cam - p
+        spec = a * max(float((to_cam / np.linalg.norm(to_cam) + 1e-12) @ refl), 0.) ** 6.
+        want = np.clip((diffuse + spec + 0.2 * a) * m + np.array([0., 0., 0.3]) * (1. - m), 0., 1.)
+        np.testing.assert_allclose(img[r, c], want, atol=2e-5)
