@@ -204,9 +204,13 @@ __global__ void __launch_bounds__(BWD_WARPS_PER_BLOCK * 32) backward_generic_ker
 
 
 // =================================================================================================
-// Fast path: C in {1,3,4} with the reference's default grouping ({1}, {3}, {3,1}).
+// The tile kernel: one launch handles one channel group of width 3 or 1 on its slice [c0, c0+C) of the cs channels, or
+// -- C = 4 -- the fused pair {3,1} of a 4-channel tensor.  Any channel count / grouping is a sequence of such launches
+// (what the reference does at the Python level, dirt/rasterise_ops.py:86-108, without slicing or copying).
 //
-// One warp per 8x8 tile, two vertically adjacent pixels per lane.
+// One warp per 8x8 tile (or per pair of tiles, see BwdTiles), two vertically adjacent pixels per lane.
+//  (0) 16x8 coverage flags written by the forward pass short-cut tiles that no face can reach:
+//      grad_background = grad_pixels, nothing else.
 //  (1) The tile of `pixels` plus its halo (10 rows x 12 columns: one pixel around for the Scharr taps and
 //      two more to the right for the flat-order reads of 1-wide groups) is staged into shared memory with
 //      cp.async, rows/columns clamped to the frame exactly as at() clamps its taps; all taps are then
@@ -220,7 +224,9 @@ __global__ void __launch_bounds__(BWD_WARPS_PER_BLOCK * 32) backward_generic_ker
 //      keeps half of the sums and hands the other half to its partner, so 21 sums need 11+6+3+2+1 = 23
 //      shuffles instead of 21*5, and every lane ends up owning one finished sum: ONE warp-wide RED per
 //      (face, tile) instead of the reference's atomicAdd per pixel per term
-//      (csrc/rasterise_grad_egl.cu:139,227-229).
+//      (csrc/rasterise_grad_egl.cu:139,227-229).  The first step works on operands (the barycentric
+//      weights are stored per half-warp), the destination of a lane's sum comes from a constant-memory
+//      table, and faces with only a few records in the tile skip the butterfly (vector REDs).
 // =================================================================================================
 
 constexpr int HALO_ROWS = TILE + 2;   // 10

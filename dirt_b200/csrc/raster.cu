@@ -1,12 +1,14 @@
-// raster.cu -- forward rasteriser: one warp per 16x8 screen tile, a 2x2 pixel quad per lane,
-// z-buffer in registers.
+// raster.cu -- forward rasteriser: one warp per CTA, two neighbouring 16x8 screen tiles per warp, a 2x2 pixel
+// quad per lane, z-buffer in registers.
 //
 // Replaces the GL draw loop + upload_background/download_pixels of the reference
 // (csrc/rasterise_egl.cpp:349-396, csrc/rasterise_egl.cu:10-38,65-91): the background is read
 // and the output written directly in the [B,H,W,C] tensors, top row first.
 //
-// Per tile, the binned face list (KIND_SMALL faces, int32 arithmetic only) and the image's large
-// list (KIND_LARGE: int64 tile-origin move; KIND_HARD: homogeneous fp64) are consumed in chunks of 32:
+// A pair of tiles with nothing binned to either is copied in one go, both tiles' loads in flight (such a tile is pure
+// latency: range -> background -> store).  Otherwise, per tile, the binned face list (KIND_SMALL faces, int32 arithmetic
+// only) and the image's large list (KIND_LARGE: int64 tile-origin move; KIND_HARD: homogeneous fp64) are consumed in
+// chunks of 32:
 //   lane phase  : one face per lane -- load its 64-B coverage record, move the three edge functions
 //                 to the tile origin, reject faces whose edge functions are negative on the whole
 //                 tile, bound the face's nearest depth key over the tile, park survivors in shared
@@ -16,6 +18,7 @@
 //                 nearest remaining bound is farther than every pixel already covered.
 // The visible face of a pixel is min (depth key, face index) -- order independent, so neither the list
 // order nor the early exit can change the result.
+// Shape choices (one warp per CTA, pairs, the form of the warp-phase loop) are measured: DESIGN.md section 4.
 #include "common.cuh"
 
 namespace dirt {
