@@ -5,7 +5,9 @@ transfers around it.  `HostRasteriser` hides them: the batch is cut into chunks 
 (copy-in, compute, copy-out) are chained with events, so the host->device copy of chunk i+1, the kernels of
 chunk i and the device->host copy of chunk i-1 overlap (PCIe is full duplex; the kernels are ~1 % of the
 transfer time).  Each chunk is one dirt_rasterise_forward + one dirt_rasterise_backward call on slices of
-preallocated device buffers.
+preallocated device buffers.  Geometry (vertices, colours, faces) is small next to the images and goes up once per step;
+the chunks carry the two image tensors each way.  Measured at BASELINE cfg3 on a B200: 12.9 ms per step against 11.1 ms
+for the same transfers with no kernels at all (bench.py, `e2e`).
 """
 import ctypes
 
