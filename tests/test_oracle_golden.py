@@ -244,3 +244,40 @@ def test_results_do_not_depend_on_the_thread_count(oracle, threads):
     np.testing.assert_array_equal(gb1, gb0)
     np.testing.assert_allclose(gv1, gv0, rtol=1e-6, atol=1e-6 * np.abs(gv0).max())
     np.testing.assert_allclose(gc1, gc0, rtol=1e-6, atol=1e-6 * np.abs(gc0).max())
+
+
+def test_position_gradient_has_the_sign_and_size_of_a_moving_square(oracle):
+    """The vertex-position gradient is an approximation by construction (Scharr edge filter + dilation, Appendix A), but
+    for a rigid shift of a bright square over a dark background under a linear loss it must come out with the right sign
+    and roughly the right size in BOTH axes -- this pins the y-up clip / row-down image convention of the gradient, which
+    no reference test asserts.  dL/dpixel = column index: shifting the 16x16 square one pixel to the right raises L by
+    16*16 (checked against the forward pass itself), i.e. dL/dx_clip = 256 * W/2 summed over the four vertices."""
+    H = W = 64
+    size, cx, cy = 16, 30.0, 32.0
+
+    def verts(cx_, cy_):
+        v = np.array([[0, 0], [0, 1], [1, 1], [1, 0]], np.float64) * size - size / 2 + [cx_, cy_]
+        v = v * 2 / np.array([W, H]) - 1
+        return np.concatenate([v, np.zeros((4, 1)), np.ones((4, 1))], 1).astype(np.float32)[None]
+
+    faces = np.array([[[0, 1, 2], [0, 2, 3]]], np.int32)
+    cols = np.ones((1, 4, 1), np.float32)
+    bg = np.zeros((1, H, W, 1), np.float32)
+    ramp_x = np.broadcast_to(np.arange(W, dtype=np.float32)[None, None, :, None], (1, H, W, 1)).copy()
+    ramp_y = np.broadcast_to(np.arange(H, dtype=np.float32)[None, :, None, None], (1, H, W, 1)).copy()
+
+    def loss(cx_, cy_, ramp):
+        return float((oracle.forward(bg, verts(cx_, cy_), cols, faces) * ramp).sum())
+
+    px = oracle.forward(bg, verts(cx, cy), cols, faces)
+    # the forward pass itself: one pixel to the right adds 256 to L; one pixel up in clip space (cy is measured in clip-y-up
+    # pixels here) moves the square to SMALLER rows and takes 256 off a row-index loss
+    assert (loss(cx + 1, cy, ramp_x) - loss(cx - 1, cy, ramp_x)) / 2 == 256.
+    assert (loss(cx, cy + 1, ramp_y) - loss(cx, cy - 1, ramp_y)) / 2 == -256.
+    _, gv, _ = oracle.backward(verts(cx, cy), faces, px, ramp_x)
+    want = 256. * W / 2
+    assert abs(gv[0, :, 0].sum() - want) < 0.1 * want and abs(gv[0, :, 1].sum()) < 0.15 * want
+    _, gv, _ = oracle.backward(verts(cx, cy), faces, px, ramp_y)
+    want = -256. * H / 2
+    assert abs(gv[0, :, 1].sum() - want) < 0.1 * abs(want) and abs(gv[0, :, 0].sum()) < 0.15 * abs(want)
+    assert (gv[..., 2] == 0).all()
