@@ -74,12 +74,14 @@ __device__ __forceinline__ V3 group_at(const float* __restrict__ pixels, int b, 
     return v;
 }
 
-// (a + b - c - d) * 3/32 + (e - f) * 10/32 in the specified order
+// (a + b - c - d) * 3/32 + (e - f) * 10/32 in the order of operations of the reference's compiled kernel
+// (csrc/rasterise_grad_egl.cu:126-127 as nvcc contracts it: FMUL (e-f)*10/32, then FFMA (a+b-c-d)*3/32 + that;
+// profiles/r02_ref_assemble_grads_scharr_sass.txt)
 __device__ __forceinline__ float scharr_comp(float a, float b, float c, float dd, float e, float f)
 {
     const float X = __fsub_rn(__fsub_rn(__fadd_rn(a, b), c), dd);
     const float Y = __fsub_rn(e, f);
-    return __fmaf_rn(Y, 0.3125f, __fmul_rn(X, 0.09375f));
+    return __fmaf_rn(X, 0.09375f, __fmul_rn(Y, 0.3125f));
 }
 
 __device__ __forceinline__ float l1(const float s[3])

@@ -489,11 +489,13 @@ static inline V3 group_at(const float* pixels, int b, int r, int c, int B, int H
 
 static inline float scharr_comp(float nn, float np, float pn, float pp, float mn, float mp)
 {
-    /* (a + b - c - d) * (3/32) + (e - f) * (10/32), the sum of products contracted as
-     * fmaf(e - f, 10/32, (a + b - c - d) * 3/32) */
+    /* (a + b - c - d) * (3/32) + (e - f) * (10/32) (csrc/rasterise_grad_egl.cu:126-127), the sum of products
+     * contracted the way nvcc contracts it when it compiles the reference file itself:
+     *     FMUL t, (e - f), 0.3125 ;  FFMA r, (a + b - c - d), 0.09375, t
+     * (oracle/_ref, SASS excerpt in profiles/r02_ref_assemble_grads_scharr_sass.txt) */
     float X = ((nn + np) - pn) - pp;
     float Y = mn - mp;
-    return fmaf(Y, 0.3125f, X * 0.09375f);
+    return fmaf(X, 0.09375f, Y * 0.3125f);
 }
 
 static void backward_image_group(const float* verts, const Tri* tris, const int32_t* ids_rows, int rb,

@@ -130,8 +130,9 @@ def assemble_grads(vertices, face_vertex_ids, gbuffer, pixels, grad_pixels):
             def scharr(a, b, c, d, e, f):
                 X = f32(f32(f32(a + b) - c) - d)
                 Y = f32(e - f)
-                # fmaf(Y, 10/32, X*3/32): emulate the single rounding in float64 (exact products)
-                return np.array([f32(np.float64(Y[i]) * 0.3125 + np.float64(f32(X[i] * f32(0.09375))))
+                # fmaf(X, 3/32, Y*10/32) -- the contraction nvcc applies to the reference file (oracle/_ref SASS);
+                # the single rounding is emulated in float64 (the products are exact there)
+                return np.array([f32(np.float64(X[i]) * 0.09375 + np.float64(f32(Y[i] * f32(0.3125))))
                                  for i in range(3)], np.float32)
 
             scharr_x = scharr(at(-1, -1), at(-1, +1), at(+1, -1), at(+1, +1), at(-1, 0), at(+1, 0))
