@@ -7,8 +7,9 @@
 A "step" is one forward + one backward pass of the hot path over one batch of synthetic scenes
 (BASELINE cfg3 by default: batch 64 per GPU, 512x512, 4-channel G-buffer, 5120-triangle icosphere with a
 pose per item), called through the C ABI of libdirt_b200.so with every buffer already resident in HBM,
-followed by the batch reduction of the vertex gradients and -- when N > 1 -- ONE NCCL all-reduce of that
-[V, 4+C] buffer (the batch shards over GPUs with no other exchange: weak scaling, 64 images per GPU).
+with the vertex gradients accumulated over the batch inside the backward kernel (DIRT_BWD_SHARED_GEOMETRY: one
+[V, 4+C] buffer) and -- when N > 1 -- ONE NCCL all-reduce of that buffer per step, issued on a side stream so that it
+overlaps the next step's forward pass (the batch shards over GPUs with no other exchange: weak scaling, 64 images per GPU).
 
 One JSON line on rank 0:  value = B_total*H*W / step time (CUDA events, max over ranks);  e2e = the same
 call with HOST (pinned) buffers, host<->device copies inside the timed region;  roofline = the dominant
@@ -56,6 +57,54 @@ def measured_peak_gbs():
             return float(json.load(f)['hbm_gbs']), 'measured (MEASURED_PEAKS.json hbm_gbs, burst copy)'
     except Exception:
         return 6650.0, 'fallback (B200_PROFILING.md: 6.65 TB/s)'
+
+
+def host_record():
+    """Who ran the CPU legs (BASELINE.md section 4 asks for it next to every CPU number)."""
+    model = None
+    try:
+        with open('/proc/cpuinfo') as f:
+            for line in f:
+                if line.lower().startswith('model name'):
+                    model = line.split(':', 1)[1].strip()
+                    break
+    except OSError:
+        pass
+    try:
+        usable = len(os.sched_getaffinity(0))
+    except AttributeError:
+        usable = os.cpu_count()
+    import socket
+    return {'hostname': socket.gethostname(), 'cpu_model': model, 'nproc': os.cpu_count(), 'usable_threads': usable}
+
+
+def bind_to_gpu_numa_node(index):
+    """Pins this process to the CPUs of the NUMA node its GPU hangs off, BEFORE any pinned buffer is allocated: Linux
+    places pages on the node of the thread that first touches them, and a pinned buffer on the far socket costs the
+    H2D / D2H copies about half their rate once several ranks copy at once (SCALE_r01: 40 -> 20 GB/s per GPU at N=8).
+    Returns what was done, for the JSON line."""
+    info = {'node': None, 'cpus': None}
+    try:
+        bdf = subprocess.run(['nvidia-smi', '-i', str(index), '--query-gpu=pci.bus_id', '--format=csv,noheader'],
+                             capture_output=True, text=True, timeout=20).stdout.strip().lower()
+        if bdf.count(':') == 2 and len(bdf.split(':')[0]) == 8:
+            bdf = bdf[4:]   # sysfs uses a 4-digit PCI domain
+        with open('/sys/bus/pci/devices/%s/numa_node' % bdf) as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return info
+        cpus = set()
+        with open('/sys/devices/system/node/node%d/cpulist' % node) as f:
+            for part in f.read().strip().split(','):
+                lo, _, hi = part.partition('-')
+                cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            info = {'node': node, 'cpus': len(cpus)}
+    except Exception as exc:   # no sysfs / nvidia-smi: run unbound
+        info['error'] = repr(exc)
+    return info
 
 
 class ClockSampler(threading.Thread):
@@ -132,13 +181,18 @@ class PreparedStep:
         self.pixels = torch.empty_like(self.background)
         self.face_ids = torch.empty((B, H, W), dtype=torch.int32, device=device)
         self.grad_background = torch.empty_like(self.background)
-        self.grad_vertices = torch.empty((B, V, 4), dtype=torch.float32, device=device)
-        self.grad_vertex_colors = torch.empty((B, V, C), dtype=torch.float32, device=device)
-        self.shared_grad = torch.empty((V, 4 + C), dtype=torch.float32, device=device)
+        # gradient of the batch-shared geometry: [V,4] | [V,C] in ONE flat buffer (what the all-reduce moves); two of
+        # them alternate so that the all-reduce of step k overlaps the kernels of step k+1
+        self.shared_flat = [torch.zeros(V * (4 + C), dtype=torch.float32, device=device) for _ in range(2)]
+        self.shared_gv = [f[:V * 4].view(V, 4) for f in self.shared_flat]
+        self.shared_gc = [f[V * 4:].view(V, C) for f in self.shared_flat]
         self.ws_bytes = int(self.lib.dirt_workspace_bytes(B, H, W, C, V, F))
         self.workspace = torch.empty(self.ws_bytes, dtype=torch.uint8, device=device)
         self.launches_per_step = 0
-        self.graph = None
+        self.graphs = None
+        self.parity = 0
+        self.comm_stream = torch.cuda.Stream(device)
+        self.comm_done = [None, None]
 
     def _p(self, t):
         return ctypes.c_void_p(t.data_ptr())
@@ -152,48 +206,72 @@ class PreparedStep:
         self._check(rc, 'Rasterise')
         return self.lib.dirt_last_launch_count()
 
-    def backward(self):
+    def backward(self, which=0):
         B, H, W, C, V, F = self.dims
         stream = ctypes.c_void_p(self.torch.cuda.current_stream(self.device).cuda_stream)
-        rc = self.lib.dirt_rasterise_backward(self._p(self.vertices), self._p(self.faces), self._p(self.pixels),
-                                              self._p(self.grad_pixels), self._p(self.face_ids), self._p(self.grad_background),
-                                              self._p(self.grad_vertices), self._p(self.grad_vertex_colors), B, H, W, C, V, F,
-                                              None, 0, 1, self._p(self.workspace), self.ws_bytes, stream)
+        # vertex gradients accumulated over the batch inside the kernel (flags = DIRT_BWD_SHARED_GEOMETRY)
+        rc = self.lib.dirt_rasterise_backward_ex(self._p(self.vertices), self._p(self.faces), self._p(self.pixels),
+                                                 self._p(self.grad_pixels), self._p(self.face_ids), self._p(self.grad_background),
+                                                 self._p(self.shared_gv[which]), self._p(self.shared_gc[which]), B, H, W, C, V, F,
+                                                 None, 0, 1, 1, self._p(self.workspace), self.ws_bytes, stream)
         self._check(rc, 'RasteriseGrad')
         return self.lib.dirt_last_launch_count()
 
-    def local_step(self):
-        """forward + backward + the shard-local reduction of the shared-geometry gradient (no collective)."""
+    def local_step(self, which=0):
+        """forward + backward, the gradient of the batch-shared geometry landing in shared_flat[which] (no collective)."""
         n = self.forward()
-        n += self.backward()
-        self.torch.sum(self.grad_vertices, dim=0, out=self.shared_grad[:, :4])
-        self.torch.sum(self.grad_vertex_colors, dim=0, out=self.shared_grad[:, 4:])
+        n += self.backward(which)
         self.launches_per_step = n
         return n
 
     def capture(self):
-        """Record local_step() into a CUDA graph (every C-ABI call only enqueues work on the given stream)."""
+        """Record local_step() into CUDA graphs, one per gradient buffer (every C-ABI call only enqueues work on the given stream)."""
         torch = self.torch
         side = torch.cuda.Stream(self.device)
         side.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(side):
-            self.local_step()
+            self.local_step(0)
         torch.cuda.current_stream(self.device).wait_stream(side)
         torch.cuda.synchronize(self.device)
-        self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
-            self.local_step()
+        self.graphs = []
+        for which in (0, 1):
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self.local_step(which)
+            self.graphs.append(g)
 
     def step(self, world):
-        if self.graph is not None:
-            self.graph.replay()
+        """One step.  With N > 1 the all-reduce of this step's [V, 4+C] buffer runs on a side stream, overlapping the next
+        step's kernels (which write the OTHER buffer); the step after that waits for it before reusing the buffer."""
+        torch = self.torch
+        which = self.parity
+        self.parity ^= 1
+        cur = torch.cuda.current_stream(self.device)
+        if world > 1 and self.comm_done[which] is not None:
+            cur.wait_event(self.comm_done[which])   # the all-reduce that last read this buffer
+        if self.graphs is not None:
+            self.graphs[which].replay()
             n = self.launches_per_step
         else:
-            n = self.local_step()
+            n = self.local_step(which)
         if world > 1:   # the one exchange of the path: all-reduce of the [V, 4+C] shared-geometry gradient
             import torch.distributed as dist
-            dist.all_reduce(self.shared_grad, op=dist.ReduceOp.SUM)
+            ready = torch.cuda.Event()
+            ready.record(cur)
+            with torch.cuda.stream(self.comm_stream):
+                self.comm_stream.wait_event(ready)
+                dist.all_reduce(self.shared_flat[which], op=dist.ReduceOp.SUM)
+                done = torch.cuda.Event()
+                done.record(self.comm_stream)
+            self.comm_done[which] = done
         return n
+
+    def drain(self):
+        """Make the current stream wait for every outstanding all-reduce (end of a timed region)."""
+        cur = self.torch.cuda.current_stream(self.device)
+        for ev in self.comm_done:
+            if ev is not None:
+                cur.wait_event(ev)
 
 
 class HostStep:
@@ -229,6 +307,42 @@ class HostStep:
             for k, t in r.h_out.items():
                 t.copy_(r.d[k], non_blocking=True)
         cur.wait_stream(r.s_in); cur.wait_stream(r.s_out)
+
+
+def check_against_oracle(prep, scene, images=1):
+    """Outside the timed region: the buffers the timed steps left behind against the CPU oracle (first `images` images)
+    and, for the batch-accumulated vertex gradients, against the per-item call summed over the batch."""
+    import torch
+    from oracle import oracle
+    from dirt_b200 import rasterise_ops as ops
+    oracle.build()
+    B, H, W, C, V, F = prep.dims
+    n = min(images, B)
+    prep.local_step(0)
+    torch.cuda.synchronize(prep.device)
+    sub = {k: np.ascontiguousarray(v[:n]) for k, v in scene.items()}
+    pixels_o, ids_o = oracle.forward(**sub, return_face_ids=True)
+    gp = prep.grad_pixels_host[:n]
+    gb_o, gv_o, gc_o = oracle.backward(sub['vertices'], sub['faces'], pixels_o, gp)
+
+    def worst(a, b):
+        a = np.asarray(a, np.float64); b = np.asarray(b, np.float64)
+        allowed = 1e-4 * np.maximum(np.maximum(np.abs(a), np.abs(b)), 1e-2 * np.abs(b).max())
+        return float((np.abs(a - b) / allowed).max())
+
+    res = {'images': n}
+    res['face_ids_equal'] = bool((prep.face_ids[:n].cpu().numpy() == ids_o).all())
+    res['pixels_err_over_tol'] = worst(prep.pixels[:n].cpu().numpy(), pixels_o)
+    res['grad_background_equal'] = bool((prep.grad_background[:n].cpu().numpy() == gb_o).all())
+    # per-item gradients of the same batch through the same library (the timed step accumulates them over the batch)
+    gb, gv, gc = ops.rasterise_backward_raw(prep.vertices, prep.faces, prep.pixels, prep.grad_pixels, prep.face_ids)
+    res['grad_vertices_err_over_tol'] = worst(gv[:n].cpu().numpy(), gv_o)
+    res['grad_vertex_colors_err_over_tol'] = worst(gc[:n].cpu().numpy(), gc_o)
+    res['shared_grad_vertices_err_over_tol'] = worst(prep.shared_gv[0].cpu().numpy(), gv.double().sum(0).cpu().numpy())
+    res['shared_grad_vertex_colors_err_over_tol'] = worst(prep.shared_gc[0].cpu().numpy(), gc.double().sum(0).cpu().numpy())
+    res['ok'] = bool(res['face_ids_equal'] and res['grad_background_equal'] and
+                     all(v <= 1.0 for k, v in res.items() if k.endswith('_over_tol')))
+    return res
 
 
 def cpu_baseline(scene, grad_pixels, sample_images, threads=None, min_seconds=10.0):
@@ -272,6 +386,8 @@ def run_ours(args):
         raise RuntimeError('bench.py needs a CUDA device (there is no CPU fallback for the product path)')
     torch.cuda.set_device(local_rank)
     device = torch.device('cuda', local_rank)
+    full_affinity = os.sched_getaffinity(0)
+    numa = bind_to_gpu_numa_node(local_rank) if not args.no_numa_bind else {'node': None, 'cpus': None}
     if world > 1:
         import datetime
         import torch.distributed as dist
@@ -305,6 +421,7 @@ def run_ours(args):
         prep.capture()
     for _ in range(max(args.warmup, 3)):
         prep.step(world)
+    prep.drain()
     sync_all()
 
     sampler = ClockSampler(local_rank) if rank == 0 else None
@@ -317,6 +434,7 @@ def run_ours(args):
     launches = 0
     for _ in range(args.steps):
         launches += prep.step(world)
+    prep.drain()   # the last steps' all-reduces finish inside the timed region
     stop.record()
     sync_all()
     elapsed_ms = start.elapsed_time(stop)
@@ -400,6 +518,11 @@ def run_ours(args):
             dist.destroy_process_group()
         return
 
+    os.sched_setaffinity(0, full_affinity)   # the CPU legs below (oracle) use every host thread again
+    checked = None
+    if args.check:
+        checked = check_against_oracle(prep, scene)
+
     peak, peak_src = measured_peak_gbs()
     fwd_bytes, bwd_bytes = algorithmic_bytes(B, H, W, C, V, F)
     if k_bwd_ms >= k_fwd_ms:
@@ -427,7 +550,7 @@ def run_ours(args):
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         mpix, n_img, reps, dt, threads = cpu_baseline(scene, prep.grad_pixels_host, args.cpu_sample)
-        cpu = {'value': mpix, 'unit': UNIT, 'cores': threads, 'kind': 'port',
+        cpu = {'value': mpix, 'unit': UNIT, 'cores': threads, 'kind': 'port', 'host': host_record(),
                'sample': 'oracle/dirt_oracle.c (OpenMP over images x row bands) fwd+bwd on the first %d images of the workload, '
                          '%d passes in %.1f s' % (n_img, reps, dt)}
 
@@ -437,13 +560,18 @@ def run_ours(args):
         'data': 'synthetic',
         'config': {'workload': desc, 'name': args.workload, 'batch_per_gpu': B, 'global_batch': B * world, 'height': H, 'width': W,
                    'channels': C, 'vertices': V, 'faces': F, 'parallelism': 'batch-sharded x%d' % world,
-                   'collective': 'all_reduce(sum over batch of grad_vertices|grad_vertex_colors, [V,%d] fp32)' % (4 + C) if world > 1 else 'none (N=1)',
+                   'collective': ('all_reduce([V,%d] fp32 gradient of the batch-shared geometry) once per step on a side stream, '
+                                  'overlapping the next step' % (4 + C)) if world > 1 else 'none (N=1)',
+                   'vertex_gradients': 'accumulated over the batch in the backward kernel (DIRT_BWD_SHARED_GEOMETRY)',
                    'background': args.background,
                    'l2': 'inputs larger than L2 (%.0f MB touched per step)' % ((fwd_bytes + bwd_bytes) / 1e6)},
         'phases_ms': {'forward_call': fwd_ms, 'backward_call': bwd_ms},
-        'gpu_launches': int(launches), 'gpu_launches_per_step': int(prep.launches_per_step), 'cuda_graph': prep.graph is not None,
-        'clocks': clocks, 'roofline': roofline,
+        'gpu_launches': int(launches), 'gpu_launches_per_step': int(prep.launches_per_step), 'cuda_graph': prep.graphs is not None,
+        'clocks': clocks, 'roofline': roofline, 'numa': numa,
     }
+    if checked is not None:
+        out['checked'] = checked['ok']
+        out['check'] = checked
     if e2e:
         out['e2e'] = e2e
     if cpu:
@@ -504,7 +632,7 @@ def run_reference(args):
                    'vertices': V, 'faces': F,
                    'note': 'the reference OpenGL/TensorFlow op cannot run in this image; this is the CPU port of its path '
                            '(oracle/dirt_oracle.c, OpenMP over images x row bands, all host threads) on a bounded sample of the same workload'},
-        'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': threads, 'kind': 'port',
+        'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': threads, 'kind': 'port', 'host': host_record(),
                          'sample': '%d images of the workload per step, %d steps' % (B, args.steps)},
         'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
@@ -548,6 +676,8 @@ def main():
     ap.add_argument('--no-graph', action='store_true', help='launch every step call by call instead of replaying a CUDA graph')
     ap.add_argument('--e2e-chunks', type=int, default=8, help='batch chunks of the host copy/compute pipeline')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--check', action='store_true', help='after timing, validate the benched buffers against the CPU oracle ("checked": true)')
+    ap.add_argument('--no-numa-bind', action='store_true', help='do not pin the process to the NUMA node of its GPU')
     args = ap.parse_args()
     if args.impl == 'reference':
         run_reference(args)

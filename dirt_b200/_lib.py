@@ -18,6 +18,10 @@ ERR_BAD_CHANNEL_GROUPS = -4
 ERR_TOO_MANY_VERTICES = -5
 ERR_CUDA = -6
 ERR_MISALIGNED = -7
+ERR_STALE_WORKSPACE = -8
+BWD_SHARED_GEOMETRY = 1
+BWD_SKIP_POSITION = 2
+BWD_SKIP_COLOUR = 4
 
 
 def lib():
@@ -42,6 +46,10 @@ def lib():
     L.dirt_rasterise_forward.argtypes = [vp] * 6 + [i] * 6 + [vp, sz, vp]
     L.dirt_rasterise_backward.restype = i
     L.dirt_rasterise_backward.argtypes = [vp] * 8 + [i] * 6 + [ctypes.POINTER(ctypes.c_int), i, i, vp, sz, vp]
+    L.dirt_rasterise_backward_ex.restype = i
+    L.dirt_rasterise_backward_ex.argtypes = [vp] * 8 + [i] * 6 + [ctypes.POINTER(ctypes.c_int), i, i, i, vp, sz, vp]
+    L.dirt_workspace_status.restype = i
+    L.dirt_workspace_status.argtypes = [vp, sz] + [i] * 6 + [vp]
     L.dirt_rasterise_visibility.restype = i
     L.dirt_rasterise_visibility.argtypes = [vp] * 4 + [i] * 5 + [vp, sz, vp]
     L.dirt_kernel_timer_enable.restype = i
@@ -52,7 +60,8 @@ def lib():
 
 
 EXPORTED_SYMBOLS = ['dirt_error_string', 'dirt_abi_version', 'dirt_workspace_bytes', 'dirt_rasterise_forward',
-                    'dirt_rasterise_backward', 'dirt_rasterise_visibility', 'dirt_last_launch_count',
+                    'dirt_rasterise_backward', 'dirt_rasterise_backward_ex', 'dirt_workspace_status',
+                    'dirt_rasterise_visibility', 'dirt_last_launch_count',
                     'dirt_kernel_timer_enable', 'dirt_kernel_timer_elapsed_ms']
 
 

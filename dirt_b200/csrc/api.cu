@@ -6,6 +6,9 @@
 
 using namespace dirt;
 
+static_assert(BWD_SHARED_GEOMETRY == DIRT_BWD_SHARED_GEOMETRY && BWD_SKIP_POSITION == DIRT_BWD_SKIP_POSITION &&
+              BWD_SKIP_COLOUR == DIRT_BWD_SKIP_COLOUR, "flag values of common.cuh and dirt_b200.h differ");
+
 static thread_local int t_last_launches = 0;
 
 extern "C" const char* dirt_error_string(int code)
@@ -20,11 +23,13 @@ extern "C" const char* dirt_error_string(int code)
         case DIRT_ERR_TOO_MANY_VERTICES: return "RasteriseGrad supports a maximum of 16777216 vertices";
         case DIRT_ERR_CUDA: return "a CUDA call or kernel launch failed";
         case DIRT_ERR_MISALIGNED: return "pointer not sufficiently aligned (workspace 256 B, vertices 16 B, others 4 B)";
+        case DIRT_ERR_STALE_WORKSPACE:
+            return "workspace_holds_setup was set, but the workspace does not hold the setup records of these (vertices, faces, sizes)";
         default: return "unknown error code";
     }
 }
 
-extern "C" int dirt_abi_version(void) { return 2; }
+extern "C" int dirt_abi_version(void) { return 3; }
 
 namespace dirt {
 KernelTimer& kernel_timer()
@@ -166,21 +171,23 @@ extern "C" int dirt_rasterise_visibility(const float* vertices, const int32_t* f
     return DIRT_OK;
 }
 
-extern "C" int dirt_rasterise_backward(const float* vertices, const int32_t* faces, const float* pixels,
-                                       const float* grad_pixels, const int32_t* face_ids, float* grad_background,
-                                       float* grad_vertices, float* grad_vertex_colors, int B, int H, int W, int C, int V,
-                                       int F, const int* channel_groups, int n_groups, int workspace_holds_setup,
-                                       void* workspace, size_t workspace_bytes, void* cuda_stream)
+static int backward_impl(const float* vertices, const int32_t* faces, const float* pixels, const float* grad_pixels,
+                         const int32_t* face_ids, float* grad_background, float* grad_vertices, float* grad_vertex_colors,
+                         int B, int H, int W, int C, int V, int F, const int* channel_groups, int n_groups,
+                         int workspace_holds_setup, int flags, void* workspace, size_t workspace_bytes, void* cuda_stream)
 {
     int launches = 0;
     t_last_launches = 0;
     if (!shape_ok(B, H, W, C, V, F)) return DIRT_ERR_BAD_SHAPE;
     if (V > (1 << 24)) return DIRT_ERR_TOO_MANY_VERTICES;
+    if (flags & ~(DIRT_BWD_SHARED_GEOMETRY | DIRT_BWD_SKIP_POSITION | DIRT_BWD_SKIP_COLOUR)) return DIRT_ERR_BAD_SHAPE;
     GroupSpec groups;
     int rc = make_groups(C, channel_groups, n_groups, &groups);
     if (rc != DIRT_OK) return rc;
     if (B == 0) return DIRT_OK;
-    if (!pixels || !grad_pixels || !grad_background) return DIRT_ERR_NULL_POINTER;
+    if (!grad_pixels) return DIRT_ERR_NULL_POINTER;
+    if (!(flags & DIRT_BWD_SKIP_POSITION) && !pixels) return DIRT_ERR_NULL_POINTER;
+    if (!(flags & DIRT_BWD_SKIP_COLOUR) && !grad_background) return DIRT_ERR_NULL_POINTER;
     if ((V > 0 && (!vertices || !grad_vertices || !grad_vertex_colors)) || (F > 0 && !faces)) return DIRT_ERR_NULL_POINTER;
     if ((uintptr_t)vertices % 16 != 0 || (uintptr_t)grad_vertices % 16 != 0) return DIRT_ERR_MISALIGNED;
     if ((uintptr_t)pixels % 4 || (uintptr_t)grad_pixels % 4 || (uintptr_t)grad_background % 4 ||
@@ -194,6 +201,7 @@ extern "C" int dirt_rasterise_backward(const float* vertices, const int32_t* fac
     const int32_t* ids = face_ids;
     // the tile coverage flags in the workspace describe `ids` when the raster kernel that produced them ran on this workspace
     const bool flags_valid = !ids || workspace_holds_setup;
+    unsigned long long expect_tag = 0;
     if (!ids) {
         // no cached visibility: re-derive it exactly as the forward pass does
         CUDA_TRY(launch_setup_and_bin(vertices, faces, ws, d, stream, &launches));
@@ -201,9 +209,47 @@ extern "C" int dirt_rasterise_backward(const float* vertices, const int32_t* fac
         ids = ws.face_ids;
     } else if (!workspace_holds_setup) {
         CUDA_TRY(launch_setup_only(vertices, faces, ws, d, stream, &launches));
+    } else {
+        // a promise: checked on the device against the tag the setup pass left in the workspace
+        expect_tag = workspace_tag(vertices, faces, B, H, W, V, F);
     }
     CUDA_TRY(launch_backward(vertices, pixels, grad_pixels, ids, grad_background, grad_vertices, grad_vertex_colors, ws, d,
-                             groups, flags_valid, stream, &launches));
+                             groups, flags_valid, flags, expect_tag, stream, &launches));
     t_last_launches = launches;
     return DIRT_OK;
+}
+
+extern "C" int dirt_rasterise_backward(const float* vertices, const int32_t* faces, const float* pixels,
+                                       const float* grad_pixels, const int32_t* face_ids, float* grad_background,
+                                       float* grad_vertices, float* grad_vertex_colors, int B, int H, int W, int C, int V,
+                                       int F, const int* channel_groups, int n_groups, int workspace_holds_setup,
+                                       void* workspace, size_t workspace_bytes, void* cuda_stream)
+{
+    return backward_impl(vertices, faces, pixels, grad_pixels, face_ids, grad_background, grad_vertices, grad_vertex_colors, B, H,
+                         W, C, V, F, channel_groups, n_groups, workspace_holds_setup, 0, workspace, workspace_bytes, cuda_stream);
+}
+
+extern "C" int dirt_rasterise_backward_ex(const float* vertices, const int32_t* faces, const float* pixels,
+                                          const float* grad_pixels, const int32_t* face_ids, float* grad_background,
+                                          float* grad_vertices, float* grad_vertex_colors, int B, int H, int W, int C, int V,
+                                          int F, const int* channel_groups, int n_groups, int workspace_holds_setup, int flags,
+                                          void* workspace, size_t workspace_bytes, void* cuda_stream)
+{
+    return backward_impl(vertices, faces, pixels, grad_pixels, face_ids, grad_background, grad_vertices, grad_vertex_colors, B, H,
+                         W, C, V, F, channel_groups, n_groups, workspace_holds_setup, flags, workspace, workspace_bytes, cuda_stream);
+}
+
+extern "C" int dirt_workspace_status(const void* workspace, size_t workspace_bytes, int B, int H, int W, int C, int V, int F,
+                                     void* cuda_stream)
+{
+    if (!shape_ok(B, H, W, C, V, F)) return DIRT_ERR_BAD_SHAPE;
+    if (B == 0) return DIRT_OK;
+    int rc = check_workspace(const_cast<void*>(workspace), workspace_bytes, B, H, W, C, V, F);
+    if (rc != DIRT_OK) return rc;
+    const Workspace ws = carve_workspace(const_cast<void*>(workspace), B, H, W, F);
+    Header h;
+    cudaStream_t stream = (cudaStream_t)cuda_stream;
+    if (cudaMemcpyAsync(&h, ws.header, sizeof(h), cudaMemcpyDeviceToHost, stream) != cudaSuccess) return DIRT_ERR_CUDA;
+    if (cudaStreamSynchronize(stream) != cudaSuccess) return DIRT_ERR_CUDA;
+    return h.error ? DIRT_ERR_STALE_WORKSPACE : DIRT_OK;
 }

@@ -1,75 +1,93 @@
-// backward.cu -- the RasteriseGrad pass: restates assemble_grads
-// (csrc/rasterise_grad_egl.cu:93-236) on top of the face-id visibility buffer.
+// backward.cu -- the RasteriseGrad pass: restates assemble_grads (csrc/rasterise_grad_egl.cu:93-236) on top of the
+// face-id visibility buffer.
 //
-// Per pixel: Scharr filter of `pixels` per channel group (frame-edge clamp), colour-gradient
-// splat with the undilated barycentrics, background gradient, occluder-edge dilation from the
-// +-1 neighbour along the dominant-gradient axis (dithered by (x+y)%2), position-gradient splat.
-// Decision quantities (Scharr sums, their L1 norms, clip_w) follow the fixed fp32 operation order
-// of DESIGN.md so that every discrete choice matches the oracle; accumulated values are ordinary fp32.
+// Per pixel: Scharr filter of `pixels` per channel group (frame-edge clamp), colour-gradient splat with the undilated
+// barycentrics, background gradient, occluder-edge dilation from the +-1 neighbour along the dominant-gradient axis
+// (dithered by (x+y)%2), position-gradient splat.  Decision quantities (Scharr sums, their L1 norms, clip_w) follow the
+// fixed fp32 operation order of DESIGN.md so that every discrete choice matches the oracle and the reference's own
+// compiled kernel (oracle/_ref); accumulated values are ordinary fp32.
+//
+// One launch handles one channel group of width 3 or 1 on its slice [c0, c0+C) of the cs channels, or -- C = 4 -- the
+// fused pair {3,1} of a 4-channel tensor.  Any channel count / grouping is a sequence of such launches (what the reference
+// does at the Python level, dirt/rasterise_ops.py:86-108, without slicing or copying).
+//
+// Shape: one warp per 8x8 tile, two vertically adjacent pixels per lane, everything the tile needs staged in the warp's
+// own slice of shared memory so that no phase waits on a chain of dependent global loads:
+//  (0) 16x8 coverage flags written by the forward pass short-cut tiles that no face can reach (grad_background =
+//      grad_pixels, nothing else).
+//  (1) The tile's 10x12 halo of `face_ids` and of `pixels` arrive by TMA (cp.async.bulk.tensor, one elected lane, one
+//      mbarrier each) -- or, for tiles touching the frame border and for tensors TMA cannot describe, by per-lane
+//      cp.async with at()'s clamping.
+//  (2) FACE TABLE: the distinct faces among the tile's 64 pixels and its 32-pixel ring get a slot each (warp match +
+//      a small open-addressing hash in shared memory); their interpolation planes and vertex positions (TriInterp +
+//      TriXY, 96 B) are copied into the table with cp.async while the Scharr sums are computed.
+//  (3) G-BUFFER TILE: every lane evaluates (barycentrics, clip_w) of its two pixels and of one ring pixel from the table
+//      and parks them in shared memory; the dilation of assemble_grads (:155-194) then only reads neighbouring entries.
+//  (4) Every per-pixel term of assemble_grads is a product  scalar * barycentric  destined for vertex k of one face:
+//      C colour scalars (grad_pixels) keyed by the pixel's own face, three position scalars (a, b, c = dL/d clip x, y, w
+//      of the fragment) keyed by the possibly dilated face.  The warp loops over the occupied slots and reduces the
+//      3*(C+3) sums of each face over its 32 lanes with a transposed butterfly (every lane ends up owning one finished
+//      sum): ONE warp-wide RED per (face, tile) instead of the reference's atomicAdd per pixel per term
+//      (csrc/rasterise_grad_egl.cu:139,227-229).  Faces with only a few records in the tile skip the butterfly
+//      (vector REDs).
+//  A tile with more distinct faces than the table holds takes the reference-shaped path (one atomic per term).
 #include "common.cuh"
+
+#include <cuda.h>
+#include <cudaTypedefs.h>
 
 namespace dirt {
 
 #ifndef DIRT_BWD_WARPS
 #define DIRT_BWD_WARPS 4
 #endif
-constexpr int BWD_WARPS_PER_BLOCK = DIRT_BWD_WARPS;
 #ifndef DIRT_ABLATE
 #define DIRT_ABLATE 0   // timing experiments only: 1 = no per-face reduction, 2 = no Scharr/dilation, 3 = both
 #endif
 #ifndef DIRT_BWD_SMALL_FACE
-#define DIRT_BWD_SMALL_FACE 12  // faces owning at most this many records in a tile are added directly (0: always reduce); profiles/r01_sweep_small_face.txt
+#define DIRT_BWD_SMALL_FACE 12  // faces owning at most this many records in a tile are added directly (0: always reduce)
 #endif
-#ifndef DIRT_BWD_SMALL_LANES
-#define DIRT_BWD_SMALL_LANES 0  // > 0: the criterion is the number of lanes holding a record of the face instead
-#endif
-// 8x8 tiles (neighbours in x, = one 16x8 tile of the coverage flags) per warp.  Measured (profiles/r01_sweep_bwd_tiles.txt):
-// pairs win for C = 3 (cfg5 backward 1.36 -> 1.26 ms: a background-only pair is copied with both tiles' loads in flight)
-// and lose for C = 4, whose larger per-pixel state spills more when the tile body sits in a loop.
-#ifndef DIRT_BWD_TILES_C4
-#define DIRT_BWD_TILES_C4 1
-#endif
-#ifndef DIRT_BWD_TILES_C3
-#define DIRT_BWD_TILES_C3 2
-#endif
-// warps per CTA (32 warps per SM resident either way: 32 / warps CTAs of <= 64 registers per thread)
-#ifndef DIRT_BWD_WARPS_C4
-#define DIRT_BWD_WARPS_C4 DIRT_BWD_WARPS
-#endif
-#ifndef DIRT_BWD_WARPS_C3
-#define DIRT_BWD_WARPS_C3 DIRT_BWD_WARPS
-#endif
-template <int C> struct BwdTiles {
-    static constexpr int value = (C == 4) ? DIRT_BWD_TILES_C4 : DIRT_BWD_TILES_C3;
-    static constexpr int warps = (C == 4) ? DIRT_BWD_WARPS_C4 : DIRT_BWD_WARPS_C3;
-};
 #ifndef DIRT_BWD_PREFETCH_GP
-#define DIRT_BWD_PREFETCH_GP 1   // measured: 0.429 -> 0.419 ms at cfg3 (profiles/r01_sweep_prefetch2.txt)
+#define DIRT_BWD_PREFETCH_GP 1
 #endif
 #ifndef DIRT_BWD_MIN_BLOCKS
-#define DIRT_BWD_MIN_BLOCKS 8   // <= 64 registers: measured best (profiles/r01_sweep_bounds.txt)
+#define DIRT_BWD_MIN_BLOCKS 8   // x 4 warps: <= 64 registers
 #endif
-constexpr int TILE = 8;   // backward tile edge: one warp per 8x8 tile, two pixels per lane
+#ifndef DIRT_BWD_SLOTS_C4
+#define DIRT_BWD_SLOTS_C4 24    // face-table slots per tile (shared memory per warp: see BwdSmem)
+#endif
+#ifndef DIRT_BWD_SLOTS_C3
+#define DIRT_BWD_SLOTS_C3 32
+#endif
+#ifndef DIRT_BWD_TMA
+#define DIRT_BWD_TMA 1
+#endif
+constexpr int TILE = 8;               // backward tile edge: one warp per 8x8 tile, two pixels per lane
+constexpr int HALO_ROWS = TILE + 2;   // 10
+constexpr int HALO_COLS = TILE + 4;   // 12: col-1 .. col+10 (one pixel around for the Scharr taps, two more to the right
+                                      // for the flat-order reads of 1-wide groups; also makes every TMA box row a multiple of 16 B)
+constexpr int GB_COLS = TILE + 2;     // 10: the G-buffer tile has no use for the two extra columns
 
 struct V3 { float x, y, z; };
 
 // at(): nearest frame pixel for out-of-range taps; three components of the channel group starting at
 // c0 (width n).  For n == 1 the reference reads "channels" 1 and 2 of a contiguous [B,H,W,1] tensor,
 // i.e. the next two pixels in flat order (0 past the end of the tensor).
-__device__ __forceinline__ V3 group_at(const float* __restrict__ pixels, int b, int r, int c, const Dims& d, int c0, int n)
+struct Frame { int B, H, W; };
+__device__ __forceinline__ V3 group_at(const float* __restrict__ pixels, int b, int r, int c, const Frame d, int cs, int c0, int n)
 {
     r = max(0, min(d.H - 1, r));
     c = max(0, min(d.W - 1, c));
     const size_t lin = ((size_t)b * d.H + r) * d.W + c;
     V3 v;
     if (n == 3) {
-        const float* p = pixels + lin * d.C + c0;
+        const float* p = pixels + lin * cs + c0;
         v.x = __ldg(p); v.y = __ldg(p + 1); v.z = __ldg(p + 2);
     } else {
         const size_t total = (size_t)d.B * d.H * d.W;
-        v.x = __ldg(pixels + lin * d.C + c0);
-        v.y = (lin + 1 < total) ? __ldg(pixels + (lin + 1) * d.C + c0) : 0.f;
-        v.z = (lin + 2 < total) ? __ldg(pixels + (lin + 2) * d.C + c0) : 0.f;
+        v.x = __ldg(pixels + lin * cs + c0);
+        v.y = (lin + 1 < total) ? __ldg(pixels + (lin + 1) * cs + c0) : 0.f;
+        v.z = (lin + 2 < total) ? __ldg(pixels + (lin + 2) * cs + c0) : 0.f;
     }
     return v;
 }
@@ -89,150 +107,50 @@ __device__ __forceinline__ float l1(const float s[3])
     return __fadd_rn(__fadd_rn(fabsf(s[0]), fabsf(s[1])), fabsf(s[2]));
 }
 
-// Generic fallback: any channel count / any grouping, one atomic per term (slow, reference-shaped).
-__global__ void __launch_bounds__(BWD_WARPS_PER_BLOCK * 32) backward_generic_kernel(
-    const float* __restrict__ vertices, const float* __restrict__ pixels, const float* __restrict__ grad_pixels,
-    const int32_t* __restrict__ face_ids, float* __restrict__ grad_background, float* __restrict__ grad_vertices,
-    float* __restrict__ grad_vertex_colors, Workspace ws, Dims d, GroupSpec groups)
+// ---- asynchronous copies ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void cp_async_16(void* smem, const void* gmem)
 {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const long long tile_global = (long long)blockIdx.x * BWD_WARPS_PER_BLOCK + warp;
-    if (tile_global >= (long long)d.B * d.btiles) return;
-    const int b = (int)(tile_global / d.btiles);
-    const int t = (int)(tile_global - (long long)b * d.btiles);
-    const int ty = t / d.btiles_x, tx = t - ty * d.btiles_x;
-    const int col = tx * TILE + (lane & 7), row0 = ty * TILE + (lane >> 3) * 2;
-    if (col >= d.W) return;
-
-    const TriInterp* itp_b = ws.itp + (size_t)b * d.F;
-    const float* verts = vertices + (size_t)b * d.V * 4;
-    const int32_t* ids = face_ids + (size_t)b * d.H * d.W;
-    float* gverts = grad_vertices + (size_t)b * d.V * 4;
-    float* gcols = grad_vertex_colors + (size_t)b * d.V * d.C;
-    const int C = d.C;
-    const float inf = __int_as_float(0x7f800000);
-
-    for (int pix = 0; pix < 2; ++pix) {
-        const int row = row0 + pix;
-        if (row >= d.H) break;
-        const size_t p = ((size_t)b * d.H + row) * d.W + col;
-        const int f_own = ids[row * d.W + col];
-        TriInterp t_own;
-        float4 g_own = make_float4(-1.f, -1.f, -1.f, inf);
-        if (f_own >= 0) {
-            t_own = load_interp(itp_b + f_own);
-            g_own = exact::gbuffer_at(t_own, col, row);
-            const int vid[3] = {t_own.v0, t_own.v1, t_own.v2};
-            const float bary[3] = {g_own.x, g_own.y, g_own.z};
-            for (int ch = 0; ch < C; ++ch) {
-                const float gp = __ldg(&grad_pixels[p * C + ch]);
-#pragma unroll
-                for (int k = 0; k < 3; ++k) atomicAdd(&gcols[(size_t)vid[k] * C + ch], gp * bary[k]);
-                grad_background[p * C + ch] = 0.f;
-            }
-        } else {
-            for (int ch = 0; ch < C; ++ch) grad_background[p * C + ch] = __ldg(&grad_pixels[p * C + ch]);
-        }
-
-        const bool interior = col > 0 && row > 0 && col < d.W - 1 && row < d.H - 1;
-        int c0 = 0;
-        for (int gi = 0; gi < groups.n; ++gi) {
-            const int n = groups.width[gi];
-            // at(ox,oy) is image (row - oy, col + ox)
-            const V3 a_mm = group_at(pixels, b, row + 1, col - 1, d, c0, n), a_mp = group_at(pixels, b, row - 1, col - 1, d, c0, n);
-            const V3 a_pm = group_at(pixels, b, row + 1, col + 1, d, c0, n), a_pp = group_at(pixels, b, row - 1, col + 1, d, c0, n);
-            const V3 a_m0 = group_at(pixels, b, row, col - 1, d, c0, n), a_p0 = group_at(pixels, b, row, col + 1, d, c0, n);
-            const V3 a_0m = group_at(pixels, b, row + 1, col, d, c0, n), a_0p = group_at(pixels, b, row - 1, col, d, c0, n);
-            float sx[3], sy[3];
-            sx[0] = scharr_comp(a_mm.x, a_mp.x, a_pm.x, a_pp.x, a_m0.x, a_p0.x);
-            sx[1] = scharr_comp(a_mm.y, a_mp.y, a_pm.y, a_pp.y, a_m0.y, a_p0.y);
-            sx[2] = scharr_comp(a_mm.z, a_mp.z, a_pm.z, a_pp.z, a_m0.z, a_p0.z);
-            sy[0] = scharr_comp(a_mm.x, a_pm.x, a_mp.x, a_pp.x, a_0m.x, a_0p.x);
-            sy[1] = scharr_comp(a_mm.y, a_pm.y, a_mp.y, a_pp.y, a_0m.y, a_0p.y);
-            sy[2] = scharr_comp(a_mm.z, a_pm.z, a_mp.z, a_pp.z, a_0m.z, a_0p.z);
-
-            int f = f_own;
-            float4 g = g_own;
-            TriInterp tf = t_own;
-            if (interior) {
-                int dx = (l1(sx) > l1(sy)) ? 1 : 0, dy = 1 - dx;  // buffer (y-up) orientation
-                if ((col + row) & 1) { dx = -dx; dy = -dy; }
-                for (int attempt = 0; attempt < 2; ++attempt) {
-                    const int nc = col + dx, nr = row - dy;
-                    const int fn = ids[nr * d.W + nc];
-                    if (fn >= 0) {
-                        const TriInterp tn = load_interp(itp_b + fn);
-                        const bool differs = (f_own < 0) || tn.v0 != t_own.v0 || tn.v1 != t_own.v1 || tn.v2 != t_own.v2;
-                        const float4 gn = exact::gbuffer_at(tn, nc, nr);
-                        if (differs && g_own.w > gn.w) {
-                            g = gn; f = fn; tf = tn;
-                            break;
-                        }
-                    }
-                    dx = -dx; dy = -dy;
-                }
-            }
-            if (f >= 0) {
-                float dLdx = 0.f, dLdy = 0.f;
-                for (int ch = 0; ch < n; ++ch) {
-                    const float gp = __ldg(&grad_pixels[p * C + c0 + ch]);
-                    dLdx += gp * sx[ch];
-                    dLdy += gp * sy[ch];
-                }
-                const int vid[3] = {tf.v0, tf.v1, tf.v2};
-                const float bary[3] = {g.x, g.y, g.z};
-                float clip_x = 0.f, clip_y = 0.f;
-#pragma unroll
-                for (int k = 0; k < 3; ++k) {
-                    const float2 xy = __ldg(reinterpret_cast<const float2*>(verts + (size_t)vid[k] * 4));
-                    clip_x += bary[k] * xy.x;
-                    clip_y += bary[k] * xy.y;
-                }
-                const float inv_w = 1.f / g.w;
-                const float dxv_dxc = 0.5f * (float)d.W * inv_w, dyv_dyc = 0.5f * (float)d.H * inv_w;
-                const float dxv_dwc = -dxv_dxc * clip_x * inv_w, dyv_dwc = -dyv_dyc * clip_y * inv_w;
-#pragma unroll
-                for (int k = 0; k < 3; ++k) {
-                    const float ax = dLdx * bary[k], ay = dLdy * bary[k];
-                    atomicAdd(&gverts[(size_t)vid[k] * 4 + 0], ax * dxv_dxc);
-                    atomicAdd(&gverts[(size_t)vid[k] * 4 + 1], ay * dyv_dyc);
-                    atomicAdd(&gverts[(size_t)vid[k] * 4 + 3], ax * dxv_dwc + ay * dyv_dwc);
-                }
-            }
-            c0 += n;
-        }
-    }
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem)), "l"(gmem) : "memory");
 }
+__device__ __forceinline__ void cp_async_4(void* smem, const void* gmem)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// generic-proxy accesses to shared memory (ours) before async-proxy ones (the next TMA write into the same buffer)
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-// =================================================================================================
-// The tile kernel: one launch handles one channel group of width 3 or 1 on its slice [c0, c0+C) of the cs channels, or
-// -- C = 4 -- the fused pair {3,1} of a 4-channel tensor.  Any channel count / grouping is a sequence of such launches
-// (what the reference does at the Python level, dirt/rasterise_ops.py:86-108, without slicing or copying).
-//
-// One warp per 8x8 tile (or per pair of tiles, see BwdTiles), two vertically adjacent pixels per lane.
-//  (0) 16x8 coverage flags written by the forward pass short-cut tiles that no face can reach:
-//      grad_background = grad_pixels, nothing else.
-//  (1) The tile of `pixels` plus its halo (10 rows x 12 columns: one pixel around for the Scharr taps and
-//      two more to the right for the flat-order reads of 1-wide groups) is staged into shared memory with
-//      cp.async, rows/columns clamped to the frame exactly as at() clamps its taps; all taps are then
-//      LDS at constant offsets.  Tiles whose halo crosses the right frame edge read the taps from global
-//      memory instead (there the flat-order reads wrap into the next row).
-//  (2) Every per-pixel term of assemble_grads is a product  scalar * barycentric  destined for vertex k
-//      of one face: C colour scalars (grad_pixels) keyed by the pixel's own face, three position scalars
-//      (a, b, c = dL/d clip x, y, w of the fragment) keyed by the possibly dilated face.
-//  (3) The warp loops over the distinct faces present in the tile (REDUX.MIN over the keys) and reduces the
-//      3*(C+3) sums of each face over its 32 lanes with a transposed butterfly: at every shuffle step a lane
-//      keeps half of the sums and hands the other half to its partner, so 21 sums need 11+6+3+2+1 = 23
-//      shuffles instead of 21*5, and every lane ends up owning one finished sum: ONE warp-wide RED per
-//      (face, tile) instead of the reference's atomicAdd per pixel per term
-//      (csrc/rasterise_grad_egl.cu:139,227-229).  The first step works on operands (the barycentric
-//      weights are stored per half-warp), the destination of a lane's sum comes from a constant-memory
-//      table, and faces with only a few records in the tile skip the butterfly (vector REDs).
-// =================================================================================================
-
-constexpr int HALO_ROWS = TILE + 2;   // 10
-constexpr int HALO_COLS = TILE + 4;   // 12: col-1 .. col+10
+// TMA: one 3-D box [1][HALO_ROWS][HALO_COLS * elems] of a [B][H][W * elems] tensor into shared memory
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* map, int x, int y, int z, uint64_t* bar)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(x), "r"(y), "r"(z), "r"(smem_u32(bar)) : "memory");
+}
 
 // 16-byte vector reduction to global memory (sm_90+): four fp32 adds in one RED
 __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d)
@@ -240,86 +158,30 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
-struct PixelTerms {      // everything one pixel contributes (fast path)
-    int key_col;         // own face (-1: uncovered)
-    int key_pos;         // face receiving the position gradient (-1: none)
-    // barycentrics (c: undilated, for the colour terms; p: of the fragment receiving the position gradient), arranged for
-    // the first butterfly step: A = the vertex whose sums this lane keeps (vertex 0 on lanes 0-15, vertex 1 on lanes
-    // 16-31), B = the one it hands to its partner, 2 = vertex 2
-    float cA, cB, c2;
-    float pA, pB, p2;
+// ---- the warp's slice of shared memory ----------------------------------------------------------------------------
+struct __align__(16) SlotRec {   // one face of the tile: interpolation planes + vertex ids + vertex positions
+    TriInterp itp;               // 64 B
+    TriXY xy;                    // 32 B
+};
+static_assert(sizeof(SlotRec) == 96, "SlotRec must be 96 bytes");
+
+template <int C, int NSLOT>
+struct BwdSmem {
+    static constexpr int PX_BYTES = HALO_ROWS * HALO_COLS * C * 4;
+    static constexpr int IDS_BYTES = HALO_ROWS * HALO_COLS * 4;
+    static constexpr int GBUF_BYTES = HALO_ROWS * GB_COLS * 16;
+    static constexpr int PX_OFF = 0;
+    // the face-id tile is dead once every lane holds its ids and slots: the G-buffer tile reuses its bytes
+    static constexpr int IDS_OFF = (PX_BYTES + 127) / 128 * 128;
+    static constexpr int GBUF_OFF = IDS_OFF;
+    static constexpr int TABLE_OFF = GBUF_OFF + (GBUF_BYTES > IDS_BYTES ? GBUF_BYTES : IDS_BYTES);
+    static constexpr int KEYS_OFF = TABLE_OFF + NSLOT * (int)sizeof(SlotRec);
+    static constexpr int BAR_OFF = (KEYS_OFF + NSLOT * 4 + 7) / 8 * 8;
+    static constexpr int BYTES = (BAR_OFF + 16 + 127) / 128 * 128;
 };
 
-struct Fragment {   // a face seen at a pixel: G-buffer entry + vertex ids
-    int face;
-    int v0, v1, v2;
-    float4 g;       // bary0, bary1, bary2, clip_w
-};
-
-__device__ __forceinline__ Fragment fragment_at(const TriInterp* __restrict__ itp_b, int face, int col, int row)
-{
-    Fragment fr;
-    fr.face = face;
-    if (face >= 0) {
-        const TriInterp t = load_interp(itp_b + face);
-        fr.v0 = t.v0; fr.v1 = t.v1; fr.v2 = t.v2;
-        fr.g = exact::gbuffer_at(t, col, row);
-    } else {
-        fr.v0 = fr.v1 = fr.v2 = -1;
-        fr.g = make_float4(-1.f, -1.f, -1.f, __int_as_float(0x7f800000));
-    }
-    return fr;
-}
-
-// dilation (csrc/rasterise_grad_egl.cu:155-194).  The preferred neighbour offset (buffer, y-up orientation) depends on
-// the group's Scharr sums; given the offset, the outcome depends on the visibility buffer only.
-// Offsets are encoded as code = dx + 3*dy with (dx,dy) in {(1,0),(-1,0),(0,1),(0,-1)}: 1, -1, 3, -3.
-__device__ __forceinline__ int dilation_code(const float (&sx)[3], const float (&sy)[3], int col, int row)
-{
-    int code = (l1(sx) > l1(sy)) ? 1 : 3;
-    if ((col + row) & 1) code = -code;
-    return code;
-}
-
-struct Neighbours { int left, right, up, down; };   // face ids at (col-1,row), (col+1,row), (col,row-1), (col,row+1)
-
-__device__ __forceinline__ Fragment dilate(const Fragment& own, int code, const Neighbours nb,
-                                           const TriInterp* __restrict__ itp_b, int col, int row, int& src)
-{
-    src = 0;
-    // code = +-1: the horizontal pair (right, left); +-3: the vertical pair (up, down).  The first attempt looks along
-    // the sign of `code`, the second one the other way.
-    const bool horiz = (unsigned)(code + 1) <= 2u;
-    const int f_plus = horiz ? nb.right : nb.up, f_minus = horiz ? nb.left : nb.down;
-#pragma unroll
-    for (int attempt = 0; attempt < 2; ++attempt) {
-        const bool minus = (code < 0) != (attempt == 1);
-        const int fn = minus ? f_minus : f_plus;
-        if (fn >= 0 && fn != own.face) {
-            // buffer offset (dx,dy) is image (col + dx, row - dy)
-            const int step = minus ? -1 : 1;
-            const Fragment n = fragment_at(itp_b, fn, horiz ? col + step : col, horiz ? row : row - step);
-            const bool differs = (own.face < 0) || n.v0 != own.v0 || n.v1 != own.v1 || n.v2 != own.v2;
-            if (differs && own.g.w > n.g.w) {
-                src = attempt ? -code : code;   // distinguishes the four neighbours, never 0
-                return n;
-            }
-        }
-    }
-    return own;
-}
-
-__device__ __forceinline__ void cp_async_16(void* smem, const void* gmem)
-{
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
-}
-__device__ __forceinline__ void cp_async_4(void* smem, const void* gmem)
-{
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
-}
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
-
-// Scharr sums of the first group (width N0) from the staged tile.  lr/lc: pixel position inside the halo tile.
+// ---- Scharr sums from the staged tile -------------------------------------------------------------------------------
+// Scharr sums of a single group (width N0) from the staged tile.  lr/lc: pixel position inside the halo tile.
 template <int C, int N0>
 __device__ __forceinline__ void scharr_smem(const float* __restrict__ tile, int lr, int lc, float (&sx)[3], float (&sy)[3])
 {
@@ -365,15 +227,16 @@ __device__ __forceinline__ void scharr_smem_c4(const float* __restrict__ tile, i
     }
 }
 
-// global-memory taps (tiles at the right frame edge): three components of group [c0, c0+N0) at the clamped pixel
-template <int C, int N0>
-__device__ __forceinline__ void scharr_global(const float* __restrict__ pixels, int b, int row, int col, const Dims& d,
+// global-memory taps (tiles at the right frame edge, where the flat-order reads of a 1-wide group wrap into the next
+// row): three components of group [c0, c0+N0) at the clamped pixel
+template <int N0>
+__device__ __forceinline__ void scharr_global(const float* __restrict__ pixels, int b, int row, int col, const Frame d, int cs,
                                               int c0, float (&sx)[3], float (&sy)[3])
 {
-    const V3 a_mm = group_at(pixels, b, row + 1, col - 1, d, c0, N0), a_mp = group_at(pixels, b, row - 1, col - 1, d, c0, N0);
-    const V3 a_pm = group_at(pixels, b, row + 1, col + 1, d, c0, N0), a_pp = group_at(pixels, b, row - 1, col + 1, d, c0, N0);
-    const V3 a_m0 = group_at(pixels, b, row, col - 1, d, c0, N0), a_p0 = group_at(pixels, b, row, col + 1, d, c0, N0);
-    const V3 a_0m = group_at(pixels, b, row + 1, col, d, c0, N0), a_0p = group_at(pixels, b, row - 1, col, d, c0, N0);
+    const V3 a_mm = group_at(pixels, b, row + 1, col - 1, d, cs, c0, N0), a_mp = group_at(pixels, b, row - 1, col - 1, d, cs, c0, N0);
+    const V3 a_pm = group_at(pixels, b, row + 1, col + 1, d, cs, c0, N0), a_pp = group_at(pixels, b, row - 1, col + 1, d, cs, c0, N0);
+    const V3 a_m0 = group_at(pixels, b, row, col - 1, d, cs, c0, N0), a_p0 = group_at(pixels, b, row, col + 1, d, cs, c0, N0);
+    const V3 a_0m = group_at(pixels, b, row + 1, col, d, cs, c0, N0), a_0p = group_at(pixels, b, row - 1, col, d, cs, c0, N0);
     sx[0] = scharr_comp(a_mm.x, a_mp.x, a_pm.x, a_pp.x, a_m0.x, a_p0.x);
     sx[1] = scharr_comp(a_mm.y, a_mp.y, a_pm.y, a_pp.y, a_m0.y, a_p0.y);
     sx[2] = scharr_comp(a_mm.z, a_mp.z, a_pm.z, a_pp.z, a_m0.z, a_p0.z);
@@ -382,6 +245,16 @@ __device__ __forceinline__ void scharr_global(const float* __restrict__ pixels, 
     sy[2] = scharr_comp(a_mm.z, a_pm.z, a_mp.z, a_pp.z, a_0m.z, a_0p.z);
 }
 
+// preferred neighbour offset of the dilation (csrc/rasterise_grad_egl.cu:185-190), as a step in the G-buffer tile:
+// buffer offset (dx,dy) is image (col + dx, row - dy), i.e. +1 / -1 along a row, -GB_COLS / +GB_COLS across rows
+__device__ __forceinline__ int dilation_step(const float (&sx)[3], const float (&sy)[3], int col, int row)
+{
+    int step = (l1(sx) > l1(sy)) ? 1 : -GB_COLS;
+    if ((col + row) & 1) step = -step;
+    return step;
+}
+
+// ---- per-face reduction -------------------------------------------------------------------------------------------
 // Transposed butterfly over the lanes that differ in bits `bit`, bit/2, ..., 1: at every step a lane keeps half of its
 // sums and hands the other half to its partner.  After STEPS steps each lane is left with OUT = ceil(N / 2^STEPS) sums.
 template <int N, int STEPS>
@@ -409,7 +282,6 @@ struct TransposedReduce {
     // is out[i] a real sum?  (checks the padding introduced at every level)
     static __host__ __device__ constexpr bool valid(int lane, int bit, int i)
     {
-        // p: position inside this level's kept half
         return TransposedReduce<H, STEPS - 1>::valid(lane, bit >> 1, i) &&
                (((lane & bit) ? H : 0) + TransposedReduce<H, STEPS - 1>::base(lane, bit >> 1) + i < N);
     }
@@ -468,129 +340,231 @@ __device__ __forceinline__ int owner_meta(int lane)
     return C == 1 ? c_owner1.meta[lane] : C == 3 ? c_owner3.meta[lane] : c_owner4.meta[lane];
 }
 
-template <int C, int BWD_TILES, int NW>
+// ---- reference-shaped path for one tile (face table overflow): one atomic per term ---------------------------------
+template <int C>
+__device__ __noinline__ void tile_generic(const float* __restrict__ vertices, const float* __restrict__ pixels,
+                                          const float* __restrict__ grad_pixels, const int32_t* __restrict__ face_ids,
+                                          float* __restrict__ gverts, float* __restrict__ gcols,   // rows of this image (or the shared rows); gcols at the group's first channel
+                                          const TriInterp* __restrict__ itp_b, const Frame d, int V, int b, int col, int row0, int cs, int c0)
+{
+    constexpr int N0 = (C == 1) ? 1 : 3;
+    constexpr int NG = (C == 4) ? 2 : 1;
+    if (col >= d.W) return;
+    const float* verts = vertices + (size_t)b * V * 4;
+    const int32_t* ids = face_ids + (size_t)b * d.H * d.W;
+    const float inf = __int_as_float(0x7f800000);
+    for (int pix = 0; pix < 2; ++pix) {
+        const int row = row0 + pix;
+        if (row >= d.H) break;
+        const size_t p = ((size_t)b * d.H + row) * d.W + col;
+        const int f_own = ids[row * d.W + col];
+        TriInterp t_own;
+        float4 g_own = make_float4(-1.f, -1.f, -1.f, inf);
+        if (f_own >= 0) {
+            t_own = load_interp(itp_b + f_own);
+            g_own = exact::gbuffer_at(t_own, col, row);
+            const int vid[3] = {t_own.v0, t_own.v1, t_own.v2};
+            const float bary[3] = {g_own.x, g_own.y, g_own.z};
+            for (int ch = 0; ch < C; ++ch) {
+                const float gp = __ldg(&grad_pixels[p * cs + c0 + ch]);
+#pragma unroll
+                for (int k = 0; k < 3; ++k) atomicAdd(&gcols[(size_t)vid[k] * cs + ch], gp * bary[k]);
+            }
+        }
+        const bool interior = col > 0 && row > 0 && col < d.W - 1 && row < d.H - 1;
+        for (int gi = 0; gi < NG; ++gi) {
+            const int g0 = c0 + (gi ? 3 : 0), n = gi ? 1 : N0;
+            float sx[3], sy[3];
+            if (n == 3) scharr_global<3>(pixels, b, row, col, d, cs, g0, sx, sy);
+            else scharr_global<1>(pixels, b, row, col, d, cs, g0, sx, sy);
+            int f = f_own;
+            float4 g = g_own;
+            TriInterp tf = t_own;
+            if (interior) {
+                int dx = (l1(sx) > l1(sy)) ? 1 : 0, dy = 1 - dx;  // buffer (y-up) orientation
+                if ((col + row) & 1) { dx = -dx; dy = -dy; }
+                for (int attempt = 0; attempt < 2; ++attempt) {
+                    const int nc = col + dx, nr = row - dy;
+                    const int fn = ids[nr * d.W + nc];
+                    if (fn >= 0) {
+                        const TriInterp tn = load_interp(itp_b + fn);
+                        const bool differs = (f_own < 0) || tn.v0 != t_own.v0 || tn.v1 != t_own.v1 || tn.v2 != t_own.v2;
+                        const float4 gn = exact::gbuffer_at(tn, nc, nr);
+                        if (differs && g_own.w > gn.w) {
+                            g = gn; f = fn; tf = tn;
+                            break;
+                        }
+                    }
+                    dx = -dx; dy = -dy;
+                }
+            }
+            if (f >= 0) {
+                float dLdx = 0.f, dLdy = 0.f;
+                for (int ch = 0; ch < n; ++ch) {
+                    const float gp = __ldg(&grad_pixels[p * cs + g0 + ch]);
+                    dLdx += gp * sx[ch];
+                    dLdy += gp * sy[ch];
+                }
+                const int vid[3] = {tf.v0, tf.v1, tf.v2};
+                const float bary[3] = {g.x, g.y, g.z};
+                float clip_x = 0.f, clip_y = 0.f;
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    const float2 xy = __ldg(reinterpret_cast<const float2*>(verts + (size_t)vid[k] * 4));
+                    clip_x += bary[k] * xy.x;
+                    clip_y += bary[k] * xy.y;
+                }
+                const float inv_w = 1.f / g.w;
+                const float dxv_dxc = 0.5f * (float)d.W * inv_w, dyv_dyc = 0.5f * (float)d.H * inv_w;
+                const float dxv_dwc = -dxv_dxc * clip_x * inv_w, dyv_dwc = -dyv_dyc * clip_y * inv_w;
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    const float ax = dLdx * bary[k], ay = dLdy * bary[k];
+                    atomicAdd(&gverts[(size_t)vid[k] * 4 + 0], ax * dxv_dxc);
+                    atomicAdd(&gverts[(size_t)vid[k] * 4 + 1], ay * dyv_dyc);
+                    atomicAdd(&gverts[(size_t)vid[k] * 4 + 3], ax * dxv_dwc + ay * dyv_dwc);
+                }
+            }
+        }
+    }
+}
+
+// G-buffer entry of a face at a pixel, from the tile's face table
+__device__ __forceinline__ float4 table_gbuffer(const SlotRec* __restrict__ table, int slot, int col, int row)
+{
+    const float4* r = reinterpret_cast<const float4*>(table + slot);
+    const float4 v0 = r[0], v1 = r[1], v2 = r[2];
+    const int4 v3 = reinterpret_cast<const int4*>(r)[3];
+    TriInterp t;
+    t.q0A = v0.x; t.q0B = v0.y; t.q0C = v0.z; t.q1A = v0.w;
+    t.q1B = v1.x; t.q1C = v1.y; t.sA = v1.z; t.sB = v1.w;
+    t.sC = v2.x; t.cref = v3.x; t.rref = v3.y;
+    return exact::gbuffer_at(t, col, row);
+}
+
+struct PixelTerms {      // everything one pixel contributes
+    int key_col;         // slot of the own face (-1: uncovered)
+    int key_pos;         // slot of the face receiving the position gradient (-1: none)
+    // barycentrics (c: undilated, for the colour terms; p: of the fragment receiving the position gradient), arranged for
+    // the first butterfly step: A = the vertex whose sums this lane keeps (vertex 0 on lanes 0-15, vertex 1 on lanes
+    // 16-31), B = the one it hands to its partner, 2 = vertex 2
+    float cA, cB, c2;
+    float pA, pB, p2;
+};
+
+template <int C, int NSLOT, int NW, bool USE_TMA>
 __global__ void __launch_bounds__(NW * 32, DIRT_BWD_MIN_BLOCKS * DIRT_BWD_WARPS / NW) backward_tile_kernel(
+    const __grid_constant__ CUtensorMap px_map, const __grid_constant__ CUtensorMap ids_map,
     const float* __restrict__ vertices, const float* __restrict__ pixels, const float* __restrict__ grad_pixels,
     const int32_t* __restrict__ face_ids, float* __restrict__ grad_background, float* __restrict__ grad_vertices,
     float* __restrict__ grad_vertex_colors, Workspace ws, Dims d, const unsigned char* __restrict__ tile_flags,
-    int cs, int c0)   // cs: channels per pixel in the tensors, c0: first channel of the group this launch handles (width C)
+    int cs, int c0,   // cs: channels per pixel in the tensors, c0: first channel of the group this launch handles (width C)
+    int flags,        // BWD_SHARED_GEOMETRY: vertex gradients accumulated over the batch ([V,.]); BWD_SKIP_POSITION / _COLOUR
+    unsigned long long expect_tag)   // != 0: the caller promised that the workspace holds the setup records with this tag
 {
+    using SM = BwdSmem<C, NSLOT>;
     constexpr int NS = C + 3;                  // scalars per pixel: C colour + (a,b,c)
     constexpr int N0 = (C == 1) ? 1 : 3;       // width of the first group
     constexpr bool TWO_GROUPS = (C == 4);      // {3,1}
     constexpr int REACH = (C == 3) ? 1 : 3;    // columns to the right of the pixel that its taps read
 
-    __shared__ __align__(16) float tile_all[NW][HALO_ROWS * HALO_COLS * C];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
 
-    // grid: x = groups of BWD_WARPS_PER_BLOCK * BWD_TILES tiles along a tile row, y = tile row, z = image
+    // grid: x = groups of NW tiles along a tile row, y = tile row, z = image
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int txb = (blockIdx.x * NW + warp) * BWD_TILES, ty = blockIdx.y;
-    if (txb >= d.btiles_x) return;
-    const int trow0 = ty * TILE;
+    const int tx = blockIdx.x * NW + warp, ty = blockIdx.y;
+    if (tx >= d.btiles_x) return;
+    unsigned char* const sm = smem_raw + warp * SM::BYTES;
+    float* const tile = reinterpret_cast<float*>(sm + SM::PX_OFF);
+    int* const ids_tile = reinterpret_cast<int*>(sm + SM::IDS_OFF);
+    float4* const gbuf = reinterpret_cast<float4*>(sm + SM::GBUF_OFF);
+    SlotRec* const table = reinterpret_cast<SlotRec*>(sm + SM::TABLE_OFF);
+    int* const keys = reinterpret_cast<int*>(sm + SM::KEYS_OFF);
+    uint64_t* const bars = reinterpret_cast<uint64_t*>(sm + SM::BAR_OFF);   // [0]: face ids, [1]: pixels
+
+    const int trow0 = ty * TILE, tcol0 = tx * TILE;
     const int lcol = lane & 7, lrow0 = (lane >> 3) * 2;
-    const int row0 = trow0 + lrow0;
+    const int row0 = trow0 + lrow0, col = tcol0 + lcol;
     const int H = d.H, W = d.W;
-    float* tile = tile_all[warp];
+    // this lane's cells: its two pixels and one cell of the 32-cell ring around the tile (corners are never read)
+    const int g0 = (lrow0 + 1) * GB_COLS + lcol + 1;                  // G-buffer tile index of pixel 0 (pixel 1: + GB_COLS)
+    const int ring_r = lane < 8 ? 0 : lane < 16 ? TILE + 1 : lane - (lane < 24 ? 15 : 23);
+    const int ring_c = lane < 8 ? lane + 1 : lane < 16 ? lane - 7 : lane < 24 ? 0 : TILE + 1;
+    // whole halo inside the frame (and the 12-wide TMA box too): no clamping, every pixel is interior
+    const bool inner = tcol0 >= 1 && trow0 >= 1 && tcol0 + HALO_COLS - 2 <= W - 1 && trow0 + TILE <= H - 1;
+    const bool use_tma = USE_TMA && inner;   // warp-uniform
+    const bool per_item = !(flags & BWD_SHARED_GEOMETRY);
+    const bool want_pos = !(flags & BWD_SKIP_POSITION), want_col = !(flags & BWD_SKIP_COLOUR);
+
+    if (expect_tag != 0 && (blockIdx.x | blockIdx.y | blockIdx.z | threadIdx.x) == 0 && ws.header->tag != expect_tag) {
+        // the workspace was not filled by a forward / visibility call on these (vertices, faces, sizes): flag it
+        // (dirt_workspace_status) and poison the result instead of returning plausible numbers
+        ws.header->error = 1;
+        if (d.V > 0) grad_vertices[0] = __int_as_float(0x7fc00000);
+    }
+    uint32_t parity_ids = 0, parity_px = 0;
+    if (USE_TMA) {
+        if (lane == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        __syncwarp();
+    }
 
     for (int b = blockIdx.z; b < d.B; b += gridDim.z) {
     const TriInterp* itp_b = ws.itp + (size_t)b * d.F;
-    const float* verts = vertices + (size_t)b * d.V * 4;
-    const int32_t* ids = face_ids + (size_t)b * H * W;
-    float* gverts = grad_vertices + (size_t)b * d.V * 4;
-    float* gcols = grad_vertex_colors + (size_t)b * d.V * cs + c0;
+    const TriXY* xy_b = ws.xy + (size_t)b * d.F;
+    float* gverts = grad_vertices + (size_t)(per_item ? b : 0) * d.V * 4;
+    float* gcols = grad_vertex_colors + (size_t)(per_item ? b : 0) * d.V * cs + c0;
     const size_t img = (size_t)b * H * W;
-    const float halfW = 0.5f * (float)W, halfH = 0.5f * (float)H;
+    const size_t p0 = img + (size_t)row0 * W + col;   // pixel 0 of this lane (pixel 1: + W)
+    const bool in0 = col < W && row0 < H, in1 = col < W && row0 + 1 < H;
 
-    if (BWD_TILES == 2) {
-    // The two 8x8 tiles of this warp are exactly one 16x8 tile of the forward pass's coverage flags.
-#if DIRT_BWD_PREFETCH_GP
-    // start the DRAM read of the pair's grad_pixels while the flag is still on its way
-    if (C == 4 && lane < 16 && trow0 + (lane >> 1) < H && (txb + (lane & 1)) * TILE < W)
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(grad_pixels + (img + (size_t)(trow0 + (lane >> 1)) * W + (txb + (lane & 1)) * TILE) * 4));
-#endif
-    // ---- background-only pair: nothing can reach an unflagged tile, grad_background = grad_pixels and we are done.
-    // Both tiles' loads are issued before the first store: such a pair is pure latency (flag -> load -> store).
-    if (tile_flags != nullptr && tile_flags[(size_t)b * d.tiles + ty * d.tiles_x + (txb >> 1)] == 0) {
-        if (C == 4) {
-            float4 v[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int row = row0 + (i & 1), col = (txb + (i >> 1)) * TILE + lcol;
-                if (col < W && row < H) v[i] = __ldg(reinterpret_cast<const float4*>(grad_pixels) + img + (size_t)row * W + col);
-            }
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int row = row0 + (i & 1), col = (txb + (i >> 1)) * TILE + lcol;
-                if (col < W && row < H) reinterpret_cast<float4*>(grad_background)[img + (size_t)row * W + col] = v[i];
-            }
-        } else {
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int row = row0 + (i & 1), col = (txb + (i >> 1)) * TILE + lcol;
-                if (col >= W || row >= H) continue;
-                const size_t p = img + (size_t)row * W + col;
-#pragma unroll
-                for (int ch = 0; ch < C; ++ch) grad_background[p * cs + c0 + ch] = __ldg(grad_pixels + p * cs + c0 + ch);
-            }
-        }
-        continue;
-    }
-    }
-    for (int sub = 0; sub < BWD_TILES; ++sub) {
-    const int tx = txb + sub;
-    if (tx >= d.btiles_x) break;
-    const int tcol0 = tx * TILE;
-    const int col = tcol0 + lcol;
-
-    if (BWD_TILES == 1) {
 #if DIRT_BWD_PREFETCH_GP
     // start the DRAM read of this tile's grad_pixels while the tile flag is still on its way
     if (C == 4 && lane < 8 && trow0 + lane < H && tcol0 < W)
         asm volatile("prefetch.global.L2 [%0];" ::"l"(grad_pixels + (img + (size_t)(trow0 + lane) * W + tcol0) * 4));
 #endif
-    // ---- background-only tiles: the forward pass flagged every 16x8 tile that shows a face or touches one that does.
-    // Nothing can reach an unflagged tile: grad_background = grad_pixels and we are done.
-    if (tile_flags != nullptr && tile_flags[(size_t)b * d.tiles + ty * d.tiles_x + (tx >> 1)] == 0) {
-#pragma unroll
-        for (int pix = 0; pix < 2; ++pix) {
-            const int row = row0 + pix;
-            if (col >= W || row >= H) continue;
-            const size_t p = img + (size_t)row * W + col;
-            if (C == 4) reinterpret_cast<float4*>(grad_background)[p] = __ldg(reinterpret_cast<const float4*>(grad_pixels) + p);
-            else {
-#pragma unroll
-                for (int ch = 0; ch < C; ++ch) grad_background[p * cs + c0 + ch] = __ldg(grad_pixels + p * cs + c0 + ch);
+    const bool flagged = tile_flags == nullptr || tile_flags[(size_t)b * d.tiles + ty * d.tiles_x + (tx >> 1)] != 0;
+
+    // ---- (1) stage the halo of face ids and pixels ------------------------------------------------------------------
+    if (flagged) {
+        if (use_tma) {
+            if (lane == 0) {
+                fence_proxy_async();
+                mbar_expect_tx(&bars[0], SM::IDS_BYTES);
+                tma_load_3d(ids_tile, &ids_map, tcol0 - 1, trow0 - 1, b, &bars[0]);
+                if (want_pos) {
+                    mbar_expect_tx(&bars[1], SM::PX_BYTES);
+                    tma_load_3d(tile, &px_map, (tcol0 - 1) * C, trow0 - 1, b, &bars[1]);
+                }
             }
+        } else {
+            for (int e = lane; e < HALO_ROWS * HALO_COLS; e += 32) {
+                const int hr = e / HALO_COLS, hc = e - hr * HALO_COLS;
+                const int r = trow0 - 1 + hr, c = tcol0 - 1 + hc;
+                if (r >= 0 && r < H && c >= 0 && c < W) cp_async_4(ids_tile + e, face_ids + img + (size_t)r * W + c);
+                else ids_tile[e] = -1;
+                if (!want_pos) continue;
+                const int rc = max(0, min(H - 1, r)), cc = max(0, min(W - 1, c));
+                const float* src = pixels + (img + (size_t)rc * W + cc) * cs + c0;
+                if (C == 4) cp_async_16(tile + e * 4, src);
+                else {
+#pragma unroll
+                    for (int ch = 0; ch < C; ++ch) cp_async_4(tile + e * C + ch, src + ch);
+                }
+            }
+            cp_async_commit();
         }
-        continue;
-    }
+        if (lane < NSLOT) keys[lane] = -1;
     }
 
-    // ---- this lane's two pixels and their six outer neighbours in the visibility buffer; grad_pixels ------------
-    // rows row0-1 .. row0+2 at column col, and columns col-1 / col+1 at rows row0, row0+1 (-1 outside the frame)
-    int id_up, id_0, id_1, id_dn, id_l0, id_r0, id_l1, id_r1;
-    if (tcol0 > 0 && trow0 > 0 && tcol0 + TILE < W && trow0 + TILE < H) {   // warp-uniform: no bounds checks needed
-        const int32_t* p0 = ids + row0 * W + col;
-        id_up = __ldg(p0 - W); id_0 = __ldg(p0); id_1 = __ldg(p0 + W); id_dn = __ldg(p0 + 2 * W);
-        id_l0 = __ldg(p0 - 1); id_r0 = __ldg(p0 + 1); id_l1 = __ldg(p0 + W - 1); id_r1 = __ldg(p0 + W + 1);
-    } else {
-        const bool col_in = col < W;
-        auto id_at = [&](int r, int c) -> int { return (r >= 0 && r < H && c >= 0 && c < W) ? __ldg(&ids[r * W + c]) : -1; };
-        id_up = col_in ? id_at(row0 - 1, col) : -1; id_0 = col_in ? id_at(row0, col) : -1;
-        id_1 = col_in ? id_at(row0 + 1, col) : -1; id_dn = col_in ? id_at(row0 + 2, col) : -1;
-        id_l0 = id_at(row0, col - 1); id_r0 = id_at(row0, col + 1);
-        id_l1 = id_at(row0 + 1, col - 1); id_r1 = id_at(row0 + 1, col + 1);
-    }
-    const Neighbours nb0 = {id_l0, id_r0, id_up, id_1};
-    const Neighbours nb1 = {id_l1, id_r1, id_0, id_dn};
+    // ---- grad_pixels of this lane's pixels; background-only tiles -----------------------------------------------------
     float gp[2][C];
 #pragma unroll
     for (int pix = 0; pix < 2; ++pix) {
-        const int row = row0 + pix;
 #pragma unroll
         for (int ch = 0; ch < C; ++ch) gp[pix][ch] = 0.f;
-        if (col >= W || row >= H) continue;
-        const size_t p = img + (size_t)row * W + col;
+        if (!(pix ? in1 : in0)) continue;
+        const size_t p = p0 + (size_t)pix * W;
         if (C == 4) {
             const float4 v = __ldg(reinterpret_cast<const float4*>(grad_pixels) + p);
             gp[pix][0] = v.x; gp[pix][1 % C] = v.y; gp[pix][2 % C] = v.z; gp[pix][3 % C] = v.w;
@@ -599,170 +573,240 @@ __global__ void __launch_bounds__(NW * 32, DIRT_BWD_MIN_BLOCKS * DIRT_BWD_WARPS 
             for (int ch = 0; ch < C; ++ch) gp[pix][ch] = __ldg(grad_pixels + p * cs + c0 + ch);
         }
     }
-
-    // ---- grad_background; does anything reach this tile? -------------------------------------------------------
-    int f_own[2];
-    bool near = false;
-#pragma unroll
-    for (int pix = 0; pix < 2; ++pix) {
-        const int row = row0 + pix;
-        f_own[pix] = -2;
-        if (col >= W || row >= H) continue;
-        const size_t p = img + (size_t)row * W + col;
-        const int f = pix ? id_1 : id_0;
+    auto store_gb = [&](int pix, bool uncovered) {
         // grad_background: grad_pixels where uncovered, 0 elsewhere (:143-148, memset :247)
+        const size_t p = p0 + (size_t)pix * W;
         if (C == 4) {
             reinterpret_cast<float4*>(grad_background)[p] =
-                f < 0 ? make_float4(gp[pix][0], gp[pix][1 % C], gp[pix][2 % C], gp[pix][3 % C]) : make_float4(0.f, 0.f, 0.f, 0.f);
+                uncovered ? make_float4(gp[pix][0], gp[pix][1 % C], gp[pix][2 % C], gp[pix][3 % C]) : make_float4(0.f, 0.f, 0.f, 0.f);
         } else {
 #pragma unroll
-            for (int ch = 0; ch < C; ++ch) grad_background[p * cs + c0 + ch] = f < 0 ? gp[pix][ch] : 0.f;
+            for (int ch = 0; ch < C; ++ch) grad_background[p * cs + c0 + ch] = uncovered ? gp[pix][ch] : 0.f;
         }
-        // own coverage, or (interior pixels only) a covered 4-neighbour that could dilate into this pixel
-        bool n = f >= 0;
-        if (!n && col > 0 && row > 0 && col < W - 1 && row < H - 1)
-            n = pix ? ((nb1.left & nb1.right & nb1.up & nb1.down) >= 0) : ((nb0.left & nb0.right & nb0.up & nb0.down) >= 0);   // any of the four non-negative
-        if (n) f_own[pix] = f;   // -2: nothing can reach this pixel
-        near = near || n;
+    };
+    if (!flagged) {
+        // the forward pass flagged every 16x8 tile that shows a face or touches one that does: nothing can reach this one
+        if (want_col && in0) store_gb(0, true);
+        if (want_col && in1) store_gb(1, true);
+        continue;
     }
-    if (!__any_sync(0xffffffffu, near)) continue;
 
-    // ---- stage the tile of `pixels` (+halo) ----------------------------------------------------------
-    const bool staged = (tcol0 + TILE - 1 + REACH) <= W - 1;   // warp-uniform
-    if (staged) {
-        constexpr int ELEMS = HALO_ROWS * HALO_COLS;
-        for (int e = lane; e < ELEMS; e += 32) {
-            const int hr = e / HALO_COLS, hc = e - hr * HALO_COLS;
-            const int r = max(0, min(H - 1, trow0 - 1 + hr));
-            const int c = max(0, min(W - 1, tcol0 - 1 + hc));
-            const float* src = pixels + (img + (size_t)r * W + c) * (C == 4 ? 4 : cs) + (C == 4 ? 0 : c0);
-            if (C == 4) cp_async_16(tile + e * 4, src);
-            else {
-#pragma unroll
-                for (int ch = 0; ch < C; ++ch) cp_async_4(tile + e * C + ch, src + ch);
+    // ---- (2) face ids -> slots of the tile's face table ---------------------------------------------------------------
+    if (use_tma) { mbar_wait(&bars[0], parity_ids); parity_ids ^= 1; }
+    else cp_async_wait_all();
+    __syncwarp();
+    const int i0 = (lrow0 + 1) * HALO_COLS + lcol + 1;
+    const int id0 = ids_tile[i0], id1 = ids_tile[i0 + HALO_COLS], idr = ids_tile[ring_r * HALO_COLS + ring_c];
+    if (want_col && in0) store_gb(0, id0 < 0);
+    if (want_col && in1) store_gb(1, id1 < 0);
+    if (!__any_sync(0xffffffffu, (id0 & id1 & idr) >= 0)) {
+        // no face in the tile or its ring
+        if (use_tma && want_pos) { mbar_wait(&bars[1], parity_px); parity_px ^= 1; }
+        continue;
+    }
+    // per pixel: covered, or (interior pixels only) a covered 4-neighbour that could dilate into it
+    bool near0, near1, interior0 = true, interior1 = true;
+    {
+        const int up0 = ids_tile[i0 - HALO_COLS], l0 = ids_tile[i0 - 1], r0 = ids_tile[i0 + 1];
+        const int l1 = ids_tile[i0 + HALO_COLS - 1], r1 = ids_tile[i0 + HALO_COLS + 1], dn1 = ids_tile[i0 + 2 * HALO_COLS];
+        if (!inner) {
+            interior0 = col > 0 && row0 > 0 && col < W - 1 && row0 < H - 1;
+            interior1 = col > 0 && row0 + 1 < H - 1 && col < W - 1;
+        }
+        near0 = id0 >= 0 || (want_pos && interior0 && (up0 & l0 & r0 & id1) >= 0);   // any of the four non-negative
+        near1 = id1 >= 0 || (want_pos && interior1 && (id0 & l1 & r1 & dn1) >= 0);
+        if (!in0) near0 = false;
+        if (!in1) near1 = false;
+    }
+    // slots: one leader per distinct id (warp match) inserts it into the open-addressing hash `keys`
+    bool overflow = false;
+    auto slot_of = [&](int id) -> int {
+        const unsigned peers = __match_any_sync(0xffffffffu, id);
+        const int leader = __ffs(peers) - 1;
+        int slot = -1;
+        if (id >= 0 && lane == leader) {
+            int h = (NSLOT == 32) ? (int)(((unsigned)id * 2654435761u) >> 27) : (int)__umulhi((unsigned)id * 2654435761u, (unsigned)NSLOT);
+            for (int probe = 0; probe < NSLOT; ++probe) {
+                const int old = atomicCAS(&keys[h], -1, id);
+                if (old == -1 || old == id) { slot = h; break; }
+                h = (h + 1 == NSLOT) ? 0 : h + 1;
             }
+            if (slot < 0) overflow = true;
         }
+        return __shfl_sync(0xffffffffu, slot, leader);
+    };
+    const int slot0 = slot_of(id0);
+    const int s1 = slot_of(id1);
+    const int slotr = slot_of(idr);
+    __syncwarp();
+    if (__any_sync(0xffffffffu, overflow)) {
+        // more distinct faces than slots: the reference-shaped path for this tile
+        if (use_tma && want_pos) { mbar_wait(&bars[1], parity_px); parity_px ^= 1; }
+        tile_generic<C>(vertices, pixels, grad_pixels, face_ids, gverts, gcols, itp_b, Frame{d.B, H, W}, d.V, b, col, row0, cs, c0);
+        __syncwarp();
+        continue;
+    }
+    // fill the table: the lane whose index is an occupied slot copies that face's 96 bytes
+    {
+        const int k = lane < NSLOT ? keys[lane] : -1;
+        if (k >= 0) {
+            const uint4* src = reinterpret_cast<const uint4*>(itp_b + k);
+            uint4* dst = reinterpret_cast<uint4*>(table + lane);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) cp_async_16(dst + i, src + i);
+            const uint4* srcx = reinterpret_cast<const uint4*>(xy_b + k);
+            cp_async_16(dst + 4, srcx);
+            cp_async_16(dst + 5, srcx + 1);
+        }
+        cp_async_commit();
     }
 
-    // ---- own fragments (overlaps the staging copies) ---------------------------------------------------
-    Fragment own[2];
-    own[0] = fragment_at(itp_b, max(f_own[0], -1), col, row0);
-    if (f_own[1] == f_own[0] && f_own[0] >= 0) {
-        // same face one row down: only the G-buffer entry changes
-        own[1] = own[0];
-        own[1].g = exact::gbuffer_at(load_interp(itp_b + f_own[1]), col, row0 + 1);
-    } else {
-        own[1] = fragment_at(itp_b, max(f_own[1], -1), col, row0 + 1);
+    // ---- (3) G-buffer tile: this lane's two pixels and its ring cell ---------------------------------------------------
+    cp_async_wait_all();
+    if (use_tma && want_pos) { mbar_wait(&bars[1], parity_px); parity_px ^= 1; }
+    __syncwarp();   // table and pixel halo complete; every lane has read its face ids (the G-buffer tile reuses their bytes)
+    const float inf = __int_as_float(0x7f800000);
+    float4 own[2];
+    own[0] = make_float4(-1.f, -1.f, -1.f, inf);
+    own[1] = own[0];
+    if (slot0 >= 0) own[0] = table_gbuffer(table, slot0, col, row0);
+    if (s1 >= 0) own[1] = table_gbuffer(table, s1, col, row0 + 1);
+    gbuf[g0] = make_float4(own[0].x, own[0].y, own[0].w, __int_as_float(slot0));
+    gbuf[g0 + GB_COLS] = make_float4(own[1].x, own[1].y, own[1].w, __int_as_float(s1));
+    {
+        float4 gr = make_float4(-1.f, -1.f, inf, __int_as_float(-1));
+        if (want_pos && slotr >= 0) {
+            const float4 t = table_gbuffer(table, slotr, tcol0 - 1 + ring_c, trow0 - 1 + ring_r);
+            gr = make_float4(t.x, t.y, t.w, __int_as_float(slotr));
+        }
+        gbuf[ring_r * GB_COLS + ring_c] = gr;
     }
-    if (staged) cp_async_wait_all();
     __syncwarp();
 
-    // ---- per-pixel terms -------------------------------------------------------------------------------------
+    // ---- dilation and per-pixel terms ---------------------------------------------------------------------------------------
+    const float halfW = 0.5f * (float)W, halfH = 0.5f * (float)H;
+    const bool staged_taps = (tcol0 + TILE - 1 + REACH) <= W - 1;   // warp-uniform (see scharr_global)
     const bool upper = (lane & 16) != 0;   // which half of the warp: decides the arrangement of the weights in PixelTerms
     PixelTerms term[2];
     float sc[2][NS];    // scalars: [0,C) grad_pixels, C..C+2 = a,b,c
 #pragma unroll
     for (int pix = 0; pix < 2; ++pix) {
-        const int row = row0 + pix;
         PixelTerms& T = term[pix];
         T.key_col = T.key_pos = -1;
         T.cA = T.cB = T.c2 = T.pA = T.pB = T.p2 = 0.f;
 #pragma unroll
         for (int i = 0; i < NS; ++i) sc[pix][i] = (i < C) ? gp[pix][i % C] : 0.f;
-        if (f_own[pix] == -2) continue;
-        const Fragment& me = own[pix];
-        const bool interior = col > 0 && row > 0 && col < W - 1 && row < H - 1;
-        T.key_col = me.face;
-        if (me.face >= 0) { T.cA = upper ? me.g.y : me.g.x; T.cB = upper ? me.g.x : me.g.y; T.c2 = me.g.z; }
+        if (!(pix ? near1 : near0)) continue;
+        const float4 me = own[pix];
+        const int my_slot = pix ? s1 : slot0;
+        const int g = g0 + pix * GB_COLS;
+        const int row = row0 + pix;
+        const bool interior = pix ? interior1 : interior0;
+        if (want_col && my_slot >= 0) { T.key_col = my_slot; T.cA = upper ? me.y : me.x; T.cB = upper ? me.x : me.y; T.c2 = me.z; }
+        if (!want_pos) continue;
 #if DIRT_ABLATE >= 2
-        T.key_pos = me.face; T.pA = T.cA; T.pB = T.cB; T.p2 = T.c2;
+        T.key_pos = my_slot; T.pA = T.cA; T.pB = T.cB; T.p2 = T.c2;
         sc[pix][C] = gp[pix][0]; sc[pix][C + 1] = gp[pix][0]; sc[pix][C + 2] = gp[pix][0];
         continue;
 #endif
-
+        // Scharr sums -> gradient scalars and dilation steps of the group(s)
         float sx[3], sy[3], sx1[3], sy1[3];
-        if (staged) {
+        if (staged_taps) {
             if (C == 4) scharr_smem_c4(tile, lrow0 + pix + 1, lcol + 1, sx, sy, sx1, sy1);
             else scharr_smem<C, N0>(tile, lrow0 + pix + 1, lcol + 1, sx, sy);
         } else {
-            scharr_global<C, N0>(pixels, b, row, col, d, c0, sx, sy);
-            if (TWO_GROUPS) scharr_global<C, 1>(pixels, b, row, col, d, c0 + 3, sx1, sy1);
+            scharr_global<N0>(pixels, b, row, col, Frame{d.B, H, W}, cs, c0, sx, sy);
+            if (TWO_GROUPS) scharr_global<1>(pixels, b, row, col, Frame{d.B, H, W}, cs, c0 + 3, sx1, sy1);
         }
-        // C = 4: reduce the Scharr sums to what the rest needs (two gradient scalars and a dilation code per group) BEFORE
-        // the dilation's loads -- twelve sums fewer live across them (0.4225 -> 0.4077 ms at cfg3).  The single-group
-        // kernels are faster with the sums consumed after the dilation (cfg5: 1.258 vs 1.308 ms), so they keep that order.
-        float dLdx = 0.f, dLdy = 0.f;
-        float gx1 = 0.f, gy1 = 0.f;
-        int code0 = 0, code1 = 0, src0 = 0;
-        Fragment pos0 = me;
+        float dLdx = 0.f, dLdy = 0.f, gx1 = 0.f, gy1 = 0.f;
+#pragma unroll
+        for (int ch = 0; ch < N0; ++ch) { dLdx += gp[pix][ch] * sx[ch]; dLdy += gp[pix][ch] * sy[ch]; }
+        const int step0 = interior ? dilation_step(sx, sy, col, row) : 0;
+        int step1 = 0;
         if (TWO_GROUPS) {
-#pragma unroll
-            for (int ch = 0; ch < N0; ++ch) { dLdx += gp[pix][ch] * sx[ch]; dLdy += gp[pix][ch] * sy[ch]; }
-            code0 = interior ? dilation_code(sx, sy, col, row) : 0;
             gx1 = gp[pix][3 % C] * sx1[0]; gy1 = gp[pix][3 % C] * sy1[0];
-            code1 = interior ? dilation_code(sx1, sy1, col, row) : 0;
-            if (interior) pos0 = dilate(me, code0, pix ? nb1 : nb0, itp_b, col, row, src0);
-        } else {
-            if (interior) {
-                code0 = dilation_code(sx, sy, col, row);
-                pos0 = dilate(me, code0, pix ? nb1 : nb0, itp_b, col, row, src0);
-            }
-#pragma unroll
-            for (int ch = 0; ch < N0; ++ch) { dLdx += gp[pix][ch] * sx[ch]; dLdy += gp[pix][ch] * sy[ch]; }
+            step1 = interior ? dilation_step(sx1, sy1, col, row) : 0;
         }
 
-        auto position_terms = [&](const Fragment& fr, float gx, float gy, float& a, float& bb, float& cc) {
-            // a = dL/dx_clip, b = dL/dy_clip, c = dL/dw_clip of the fragment (:196-232)
-            const float2 p0 = __ldg(reinterpret_cast<const float2*>(verts + (size_t)fr.v0 * 4));
-            const float2 p1 = __ldg(reinterpret_cast<const float2*>(verts + (size_t)fr.v1 * 4));
-            const float2 p2 = __ldg(reinterpret_cast<const float2*>(verts + (size_t)fr.v2 * 4));
-            const float clip_x = fr.g.x * p0.x + fr.g.y * p1.x + fr.g.z * p2.x;
-            const float clip_y = fr.g.x * p0.y + fr.g.y * p1.y + fr.g.z * p2.y;
-            const float inv_w = __fdividef(1.0f, fr.g.w);
+        // dilation (:155-194): the neighbour at +step, else the one at -step, replaces this pixel's fragment if it is
+        // covered, is a different triangle (vertex triple) and is nearer.  Returns the G-buffer cell the fragment comes from.
+        auto dilate = [&](int step) -> int {
+            if (step == 0) return g;
+#pragma unroll
+            for (int attempt = 0; attempt < 2; ++attempt) {
+                const int cell = attempt ? g - step : g + step;
+                const float4 e = gbuf[cell];
+                const int ns = __float_as_int(e.w);
+                if (ns >= 0 && ns != my_slot && me.w > e.z) {
+                    bool differs = my_slot < 0;
+                    if (!differs) {
+                        const int4 a = reinterpret_cast<const int4*>(table + ns)[2], bb = reinterpret_cast<const int4*>(table + my_slot)[2];
+                        differs = a.y != bb.y || a.z != bb.z || a.w != bb.w;   // {sC, v0, v1, v2}
+                    }
+                    if (differs) return cell;
+                }
+            }
+            return g;
+        };
+        auto position_terms = [&](const float4 fr, int slot, float gx, float gy, float& a, float& bb, float& cc) {
+            // a = dL/dx_clip, b = dL/dy_clip, c = dL/dw_clip of the fragment (:196-232); fr = (b0, b1, b2, clip_w)
+            const float4 q0 = reinterpret_cast<const float4*>(table + slot)[4];   // x0 y0 x1 y1
+            const float2 q1 = reinterpret_cast<const float2*>(table + slot)[10];  // x2 y2
+            const float clip_x = fr.x * q0.x + fr.y * q0.z + fr.z * q1.x;
+            const float clip_y = fr.x * q0.y + fr.y * q0.w + fr.z * q1.y;
+            const float inv_w = __fdividef(1.0f, fr.w);
             a = gx * halfW * inv_w;
             bb = gy * halfH * inv_w;
             cc = -(a * clip_x + bb * clip_y) * inv_w;
         };
+        auto fragment_of = [&](int cell, int& slot) -> float4 {
+            if (cell == g) { slot = my_slot; return me; }
+            const float4 e = gbuf[cell];
+            slot = __float_as_int(e.w);
+            return make_float4(e.x, e.y, __fsub_rn(__fsub_rn(1.0f, e.x), e.y), e.z);
+        };
 
+        const int cell0 = dilate(step0);
+        float gx = dLdx, gy = dLdy;
         if (TWO_GROUPS) {
             // the second group dilates to the same fragment whenever it prefers the same neighbour (the usual case):
-            // the outcome of a dilation depends on the offset and on the visibility buffer only
-            if (code1 == code0) {
-                dLdx += gx1; dLdy += gy1;
+            // the outcome of a dilation depends on the step and on the visibility buffer only
+            const int cell1 = (step1 == step0) ? cell0 : dilate(step1);
+            if (cell1 == cell0) {
+                gx += gx1; gy += gy1;
             } else {
-                int src1;
-                const Fragment pos1 = dilate(me, code1, pix ? nb1 : nb0, itp_b, col, row, src1);
-                if (pos1.face >= 0) {
-                    if (pos1.face == pos0.face && src1 == src0) {
-                        dLdx += gx1; dLdy += gy1;
-                    } else {
-                        // the two groups dilated differently (rare): this group's terms go out one by one
-                        float a1, b1, c1;
-                        position_terms(pos1, gx1, gy1, a1, b1, c1);
-                        const int vid[3] = {pos1.v0, pos1.v1, pos1.v2};
-                        const float bary[3] = {pos1.g.x, pos1.g.y, pos1.g.z};
+                // the two groups dilated differently (rare): this group's terms go out one by one
+                int slot_b;
+                const float4 fr = fragment_of(cell1, slot_b);
+                if (slot_b >= 0) {
+                    float a1, b1, c1;
+                    position_terms(fr, slot_b, gx1, gy1, a1, b1, c1);
+                    const int4 q = reinterpret_cast<const int4*>(table + slot_b)[2];   // {sC, v0, v1, v2}
+                    const int vid[3] = {q.y, q.z, q.w};
+                    const float bary[3] = {fr.x, fr.y, fr.z};
 #pragma unroll
-                        for (int k = 0; k < 3; ++k) {
-                            atomicAdd(&gverts[(size_t)vid[k] * 4 + 0], a1 * bary[k]);
-                            atomicAdd(&gverts[(size_t)vid[k] * 4 + 1], b1 * bary[k]);
-                            atomicAdd(&gverts[(size_t)vid[k] * 4 + 3], c1 * bary[k]);
-                        }
+                    for (int k = 0; k < 3; ++k) {
+                        atomicAdd(&gverts[(size_t)vid[k] * 4 + 0], a1 * bary[k]);
+                        atomicAdd(&gverts[(size_t)vid[k] * 4 + 1], b1 * bary[k]);
+                        atomicAdd(&gverts[(size_t)vid[k] * 4 + 3], c1 * bary[k]);
                     }
                 }
             }
         }
-        if (pos0.face >= 0) {
-            T.key_pos = pos0.face;
-            T.pA = upper ? pos0.g.y : pos0.g.x; T.pB = upper ? pos0.g.x : pos0.g.y; T.p2 = pos0.g.z;
-            position_terms(pos0, dLdx, dLdy, sc[pix][C], sc[pix][C + 1], sc[pix][C + 2]);
+        int slot_a;
+        const float4 fr = fragment_of(cell0, slot_a);
+        if (slot_a >= 0) {
+            T.key_pos = slot_a;
+            T.pA = upper ? fr.y : fr.x; T.pB = upper ? fr.x : fr.y; T.p2 = fr.z;
+            position_terms(fr, slot_a, gx, gy, sc[pix][C], sc[pix][C + 1], sc[pix][C + 2]);
         }
     }
 
-    // ---- per-face reduction -------------------------------------------------------------------------------------
-    // One iteration per distinct face of the tile (REDUX.MIN over the keys): the 3*(C+3) sums of the face are reduced
-    // over the 32 lanes with a transposed butterfly (each lane ends up owning one finished sum) and leave the SM as ONE
-    // warp-wide RED.  Faces that own only a few records in this tile skip the butterfly: their records are added
-    // directly, all such faces of the tile together, in one pass of vector REDs at the end.
+    // ---- (4) per-face reduction -----------------------------------------------------------------------------------------
+    // One iteration per occupied slot: the 3*(C+3) sums of the face are reduced over the 32 lanes with a transposed
+    // butterfly (each lane ends up owning one finished sum) and leave the SM as ONE warp-wide RED.  Faces that own only a
+    // few records in this tile skip the butterfly: their records are added directly, all such faces of the tile together,
+    // in one pass of vector REDs at the end.
 #if DIRT_ABLATE != 1
     {
         const int owner = owner_meta<C>(lane);
@@ -771,29 +815,16 @@ __global__ void __launch_bounds__(NW * 32, DIRT_BWD_MIN_BLOCKS * DIRT_BWD_WARPS 
         const int owner_stride = (owner & 16) ? 4 : (C == 4 ? 4 : cs);
         const int kc0 = term[0].key_col, kc1 = term[1].key_col, kp0 = term[0].key_pos, kp1 = term[1].key_pos;
         unsigned direct = 0;   // bit 0/1: colour record of pixel 0/1, bit 2/3: position record of pixel 0/1
-        int last = -1;
-        while (true) {
-            // next distinct face key greater than `last`
-            unsigned cand = 0x7fffffffu;
-            if (kc0 > last) cand = min(cand, (unsigned)kc0);
-            if (kc1 > last) cand = min(cand, (unsigned)kc1);
-            if (kp0 > last) cand = min(cand, (unsigned)kp0);
-            if (kp1 > last) cand = min(cand, (unsigned)kp1);
-            const unsigned fmin = __reduce_min_sync(0xffffffffu, cand);
-            if (fmin == 0x7fffffffu) break;
-            const int f = (int)fmin;
-            last = f;
-            const bool mc0 = kc0 == f, mc1 = kc1 == f, mp0 = kp0 == f, mp1 = kp1 == f;
-#if DIRT_BWD_SMALL_FACE > 0
-#if DIRT_BWD_SMALL_LANES > 0
-            // lanes holding a record of this face (each holds up to four): one vote instead of four
-            const int records = __popc(__ballot_sync(0xffffffffu, mc0 | mc1 | mp0 | mp1));
-            if (records <= DIRT_BWD_SMALL_LANES) {
-#else
+        unsigned occupied = __ballot_sync(0xffffffffu, lane < NSLOT && keys[lane] >= 0);
+        while (occupied) {
+            const int s = __ffs(occupied) - 1;
+            occupied &= occupied - 1;
+            const bool mc0 = kc0 == s, mc1 = kc1 == s, mp0 = kp0 == s, mp1 = kp1 == s;
             const int records = __popc(__ballot_sync(0xffffffffu, mc0)) + __popc(__ballot_sync(0xffffffffu, mc1)) +
                                 __popc(__ballot_sync(0xffffffffu, mp0)) + __popc(__ballot_sync(0xffffffffu, mp1));
+            if (records == 0) continue;   // a face of the ring that nothing dilates from
+#if DIRT_BWD_SMALL_FACE > 0
             if (records <= DIRT_BWD_SMALL_FACE) {
-#endif
                 direct |= (mc0 ? 1u : 0u) | (mc1 ? 2u : 0u) | (mp0 ? 4u : 0u) | (mp1 ? 8u : 0u);
                 continue;
             }
@@ -829,7 +860,7 @@ __global__ void __launch_bounds__(NW * 32, DIRT_BWD_MIN_BLOCKS * DIRT_BWD_WARPS 
             float total[1];
             TransposedReduce<NS + H2, 4>::run(v, lane, 8, total);
             if (owner >= 0) {
-                const int4 q = __ldg(reinterpret_cast<const int4*>(itp_b + f) + 2);   // {sC, v0, v1, v2}
+                const int4 q = reinterpret_cast<const int4*>(table + s)[2];   // {sC, v0, v1, v2}
                 const int vid = (owner & 1) ? q.z : ((owner & 2) ? q.w : q.y);
                 atomicAdd(owner_row + (size_t)vid * owner_stride, total[0]);
             }
@@ -842,8 +873,8 @@ __global__ void __launch_bounds__(NW * 32, DIRT_BWD_MIN_BLOCKS * DIRT_BWD_WARPS 
                 const int pix = rec & 1;
                 const PixelTerms& T = term[pix];
                 const bool colour = rec < 2;
-                const int f = colour ? T.key_col : T.key_pos;
-                const int4 q = __ldg(reinterpret_cast<const int4*>(itp_b + f) + 2);
+                const int s = colour ? T.key_col : T.key_pos;
+                const int4 q = reinterpret_cast<const int4*>(table + s)[2];
                 const int vid[3] = {q.y, q.z, q.w};
                 const float wA = colour ? T.cA : T.pA, wB = colour ? T.cB : T.pB;
                 const float w[3] = {upper ? wB : wA, upper ? wA : wB, colour ? T.c2 : T.p2};
@@ -864,18 +895,69 @@ __global__ void __launch_bounds__(NW * 32, DIRT_BWD_MIN_BLOCKS * DIRT_BWD_WARPS 
 #endif
     }
 #endif
-    }   // sub
+    __syncwarp();   // the next image's staging overwrites the tile buffers
     }   // b
+}
+
+// ---- host side --------------------------------------------------------------------------------------------------------
+static PFN_cuTensorMapEncodeTiled tensor_map_encoder()
+{
+    static PFN_cuTensorMapEncodeTiled fn = []() -> PFN_cuTensorMapEncodeTiled {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+            return nullptr;
+        return reinterpret_cast<PFN_cuTensorMapEncodeTiled>(p);
+    }();
+    return fn;
+}
+
+// [B][H][W*elems] tensor of 4-byte elements, box [1][HALO_ROWS][HALO_COLS*elems]
+static bool make_tile_map(CUtensorMap* map, const void* base, CUtensorMapDataType type, int B, int H, int W, int elems)
+{
+    PFN_cuTensorMapEncodeTiled enc = tensor_map_encoder();
+    if (!enc) return false;
+    const cuuint64_t dims[3] = {(cuuint64_t)W * elems, (cuuint64_t)H, (cuuint64_t)B};
+    const cuuint64_t strides[2] = {(cuuint64_t)W * elems * 4, (cuuint64_t)H * W * elems * 4};
+    const cuuint32_t box[3] = {(cuuint32_t)(HALO_COLS * elems), (cuuint32_t)HALO_ROWS, 1u};
+    const cuuint32_t estr[3] = {1u, 1u, 1u};
+    return enc(map, type, 3, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <int C, int NSLOT, bool USE_TMA>
+static cudaError_t launch_tile_kernel(const CUtensorMap& px_map, const CUtensorMap& ids_map, const float* vertices,
+                                      const float* pixels, const float* grad_pixels, const int32_t* face_ids,
+                                      float* grad_background, float* grad_vertices, float* grad_vertex_colors,
+                                      const Workspace& ws, const Dims& d, const unsigned char* tflags, int cs, int c0,
+                                      int flags, unsigned long long expect_tag, cudaStream_t stream)
+{
+    constexpr int NW = DIRT_BWD_WARPS;
+    auto kernel = backward_tile_kernel<C, NSLOT, NW, USE_TMA>;
+    constexpr int smem = BwdSmem<C, NSLOT>::BYTES * NW;
+    static bool configured = false;   // per instantiation
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    const dim3 grid((unsigned)((d.btiles_x + NW - 1) / NW), (unsigned)d.btiles_y, (unsigned)min(d.B, 65535));
+    kernel<<<grid, NW * 32, smem, stream>>>(px_map, ids_map, vertices, pixels, grad_pixels, face_ids, grad_background,
+                                            grad_vertices, grad_vertex_colors, ws, d, tflags, cs, c0, flags, expect_tag);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_backward(const float* vertices, const float* pixels, const float* grad_pixels,
                             const int32_t* face_ids, float* grad_background, float* grad_vertices,
                             float* grad_vertex_colors, const Workspace& ws, const Dims& d, const GroupSpec& groups,
-                            bool tile_flags_valid, cudaStream_t stream, int* launches)
+                            bool tile_flags_valid, int flags, unsigned long long expect_tag, cudaStream_t stream, int* launches)
 {
     cudaError_t e;
-    if ((e = cudaMemsetAsync(grad_vertices, 0, sizeof(float) * (size_t)d.B * d.V * 4, stream)) != cudaSuccess) return e;
-    if ((e = cudaMemsetAsync(grad_vertex_colors, 0, sizeof(float) * (size_t)d.B * d.V * d.C, stream)) != cudaSuccess) return e;
+    const size_t rows = (size_t)((flags & BWD_SHARED_GEOMETRY) ? 1 : d.B) * d.V;
+    if ((e = cudaMemsetAsync(grad_vertices, 0, sizeof(float) * rows * 4, stream)) != cudaSuccess) return e;
+    if ((e = cudaMemsetAsync(grad_vertex_colors, 0, sizeof(float) * rows * d.C, stream)) != cudaSuccess) return e;
     const long long total_tiles = (long long)d.B * d.btiles;
     if (total_tiles == 0) return cudaSuccess;
     ScopedKernelTimer timer(2, stream);
@@ -884,42 +966,35 @@ cudaError_t launch_backward(const float* vertices, const float* pixels, const fl
     // (dirt/rasterise_ops.py:86-108), except that nothing is sliced or copied and grad_vertices accumulates in place.
     const bool fused4 = d.C == 4 && groups.n == 2 && groups.width[0] == 3 && groups.width[1] == 1 &&
                         (((uintptr_t)pixels | (uintptr_t)grad_pixels | (uintptr_t)grad_background | (uintptr_t)grad_vertex_colors) % 16 == 0);
-    const unsigned char* flags = tile_flags_valid ? ws.tile_flags : nullptr;
-    auto grid_for = [&](int tiles_per_warp, int warps) {
-        return dim3((unsigned)((d.btiles_x + warps * tiles_per_warp - 1) / (warps * tiles_per_warp)), (unsigned)d.btiles_y,
-                    (unsigned)min(d.B, 65535));
-    };
-#ifdef DIRT_FORCE_GENERIC_BACKWARD   // the reference-shaped kernel (one atomic per term), kept for debugging
-    {
-        const unsigned grid = (unsigned)((total_tiles + BWD_WARPS_PER_BLOCK - 1) / BWD_WARPS_PER_BLOCK);
-        backward_generic_kernel<<<grid, BWD_WARPS_PER_BLOCK * 32, 0, stream>>>(vertices, pixels, grad_pixels, face_ids, grad_background,
-                                                                              grad_vertices, grad_vertex_colors, ws, d, groups);
-        ++*launches;
-        return cudaGetLastError();
-    }
-#endif
+    const unsigned char* tflags = tile_flags_valid ? ws.tile_flags : nullptr;
+    // TMA staging needs tensors it can describe: the group is the whole pixel (cs == C), rows are multiples of 16 bytes
+    // and the bases 16-byte aligned; everything else is staged with per-lane cp.async
+    CUtensorMap px_map, ids_map;
+    memset(&px_map, 0, sizeof(px_map));
+    memset(&ids_map, 0, sizeof(ids_map));
+    if (!(flags & BWD_SKIP_POSITION) && !pixels) return cudaErrorInvalidValue;
+    bool tma = DIRT_BWD_TMA && pixels && (d.C == 1 || d.C == 3 || fused4) && groups.n == (fused4 ? 2 : 1) && d.W % 4 == 0 &&
+               ((uintptr_t)pixels % 16 == 0) && ((uintptr_t)face_ids % 16 == 0);
+    if (tma)
+        tma = make_tile_map(&px_map, pixels, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, d.B, d.H, d.W, d.C) &&
+              make_tile_map(&ids_map, face_ids, CU_TENSOR_MAP_DATA_TYPE_INT32, d.B, d.H, d.W, 1);
+#define DIRT_LAUNCH(CC, NSLOT, c0)                                                                                             \
+    (tma ? launch_tile_kernel<CC, NSLOT, true>(px_map, ids_map, vertices, pixels, grad_pixels, face_ids, grad_background,       \
+                                               grad_vertices, grad_vertex_colors, ws, d, tflags, d.C, c0, flags, expect_tag, stream)               \
+         : launch_tile_kernel<CC, NSLOT, false>(px_map, ids_map, vertices, pixels, grad_pixels, face_ids, grad_background,      \
+                                                grad_vertices, grad_vertex_colors, ws, d, tflags, d.C, c0, flags, expect_tag, stream))
     if (fused4) {
-        backward_tile_kernel<4, BwdTiles<4>::value, BwdTiles<4>::warps>
-            <<<grid_for(BwdTiles<4>::value, BwdTiles<4>::warps), BwdTiles<4>::warps * 32, 0, stream>>>(
-                vertices, pixels, grad_pixels, face_ids, grad_background, grad_vertices, grad_vertex_colors, ws, d, flags, 4, 0);
         ++*launches;
-        return cudaGetLastError();
+        return DIRT_LAUNCH(4, DIRT_BWD_SLOTS_C4, 0);
     }
     int c0 = 0;
     for (int g = 0; g < groups.n; ++g) {
-        if (groups.width[g] == 3)
-            backward_tile_kernel<3, BwdTiles<3>::value, BwdTiles<3>::warps>
-                <<<grid_for(BwdTiles<3>::value, BwdTiles<3>::warps), BwdTiles<3>::warps * 32, 0, stream>>>(
-                    vertices, pixels, grad_pixels, face_ids, grad_background, grad_vertices, grad_vertex_colors, ws, d, flags, d.C, c0);
-        else
-            backward_tile_kernel<1, BwdTiles<1>::value, BwdTiles<1>::warps>
-                <<<grid_for(BwdTiles<1>::value, BwdTiles<1>::warps), BwdTiles<1>::warps * 32, 0, stream>>>(
-                    vertices, pixels, grad_pixels, face_ids, grad_background, grad_vertices, grad_vertex_colors, ws, d, flags, d.C, c0);
+        const cudaError_t le = groups.width[g] == 3 ? DIRT_LAUNCH(3, DIRT_BWD_SLOTS_C3, c0) : DIRT_LAUNCH(1, DIRT_BWD_SLOTS_C3, c0);
         c0 += groups.width[g];
         ++*launches;
-        const cudaError_t le = cudaGetLastError();
         if (le != cudaSuccess) return le;
     }
+#undef DIRT_LAUNCH
     return cudaSuccess;
 }
 

@@ -49,10 +49,35 @@ struct __align__(16) TriInterp { // interpolation planes relative to (cref,rref)
 };
 static_assert(sizeof(TriInterp) == 64, "TriInterp must be 64 bytes");
 
+struct __align__(16) TriXY {     // clip-space x,y of the face's three vertices (the backward pass's clip_x / clip_y,
+    float x0, y0, x1, y1;        // csrc/rasterise_grad_egl.cu:210-215): stored next to the planes so that a tile's face
+    float x2, y2, pad0, pad1;    // table is filled in one hop
+};
+static_assert(sizeof(TriXY) == 32, "TriXY must be 32 bytes");
+
 // ---- workspace ---------------------------------------------------------------------------------
+struct Header {
+    unsigned long long tag;   // workspace_tag() of the call that filled the setup records (0: none)
+    int error;                // set by a backward call that was promised setup records which are not there
+    int pad;
+};
+
+__host__ __device__ inline unsigned long long workspace_tag(const void* vertices, const void* faces, int B, int H, int W, int V, int F)
+{
+    // FNV-1a over the identity of the geometry tensors and the sizes; never 0
+    unsigned long long h = 1469598103934665603ull;
+    const unsigned long long words[7] = {(unsigned long long)(uintptr_t)vertices, (unsigned long long)(uintptr_t)faces,
+                                         (unsigned long long)B, (unsigned long long)H, (unsigned long long)W,
+                                         (unsigned long long)V, (unsigned long long)F};
+    for (int i = 0; i < 7; ++i)
+        for (int k = 0; k < 8; ++k) { h ^= (words[i] >> (8 * k)) & 0xffull; h *= 1099511628211ull; }
+    return h ? h : 1ull;
+}
+
 struct Workspace {
     TriCov* cov;          // [B*F]
     TriInterp* itp;       // [B*F]
+    TriXY* xy;            // [B*F]
     uint2* tri_bin;       // [B*F]  tile bbox (tx0|ty0<<16, tx1|ty1<<16); x = 0xFFFFFFFF: not binned per tile
     int* tile_count;      // [B*T]  per-tile reference count, then reused as the fill cursor
     unsigned char* tile_flags;  // [B*T]  1 if the 16x8 tile or one of its 8 neighbours shows a face (written by the raster kernel)
@@ -60,9 +85,10 @@ struct Workspace {
     int* large_count;     // [B]
     int* large_list;      // [B*F]
     int* pool_cursor;     // [1] (+ padding)
+    struct Header* header; // identity of the (vertices, faces, sizes) the setup records belong to; error flag
     int* refs;            // [SMALL_TILE_LIMIT*B*F]
     int32_t* face_ids;    // [B*H*W] (used when the caller does not supply a buffer)
-    size_t zero_bytes;    // bytes from tile_count that the forward pass zeroes (counts, flags, large counts, cursor)
+    size_t zero_bytes;    // bytes from tile_count that the forward pass zeroes (counts, flags, large counts, cursor, header)
     size_t bytes;
 };
 
@@ -78,12 +104,14 @@ inline Workspace carve_workspace(void* base, int B, int H, int W, int F)
     auto take = [&](size_t bytes) { char* r = p + off; off = align_up(off + bytes, 256); return r; };
     ws.cov = (TriCov*)take(BF * sizeof(TriCov));
     ws.itp = (TriInterp*)take(BF * sizeof(TriInterp));
+    ws.xy = (TriXY*)take(BF * sizeof(TriXY));
     ws.tri_bin = (uint2*)take(BF * sizeof(uint2));
     // the four blocks the forward pass must zero are adjacent: one memset covers [tile_count, zero_end)
     ws.tile_count = (int*)take(BT * sizeof(int));
     ws.tile_flags = (unsigned char*)take(BT);
     ws.large_count = (int*)take((size_t)B * sizeof(int));
     ws.pool_cursor = (int*)take(256);
+    ws.header = (Header*)take(256);
     ws.zero_bytes = (size_t)((p + off) - (char*)ws.tile_count);
     ws.tile_range = (int2*)take(BT * sizeof(int2));
     ws.large_list = (int*)take(BF * sizeof(int));
@@ -277,6 +305,7 @@ struct ScopedKernelTimer {
 
 // ---- host-side launchers (one per .cu) ----------------------------------------------------------
 // All return cudaError_t of the launch and add the number of kernels they launched to *launches.
+// Both setup launchers leave workspace_tag(vertices, faces, sizes) in the workspace header.
 cudaError_t launch_setup_and_bin(const float* vertices, const int32_t* faces, const Workspace& ws, const Dims& d,
                                  cudaStream_t stream, int* launches);
 cudaError_t launch_setup_only(const float* vertices, const int32_t* faces, const Workspace& ws, const Dims& d,
@@ -289,6 +318,9 @@ cudaError_t launch_raster_visibility(const float* vertices, int32_t* face_ids, f
 cudaError_t launch_backward(const float* vertices, const float* pixels, const float* grad_pixels,
                             const int32_t* face_ids, float* grad_background, float* grad_vertices,
                             float* grad_vertex_colors, const Workspace& ws, const Dims& d, const GroupSpec& groups,
-                            bool tile_flags_valid, cudaStream_t stream, int* launches);
+                            bool tile_flags_valid, int flags, unsigned long long expect_tag, cudaStream_t stream,
+                            int* launches);   // flags: DIRT_BWD_* of include/dirt_b200.h; expect_tag != 0: the records are
+                                              // promised to carry this tag (checked on the device)
+constexpr int BWD_SHARED_GEOMETRY = 1, BWD_SKIP_POSITION = 2, BWD_SKIP_COLOUR = 4;   // == DIRT_BWD_* (static_assert in api.cu)
 
 }  // namespace dirt

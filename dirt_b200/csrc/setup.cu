@@ -30,6 +30,7 @@ __global__ void __launch_bounds__(DIRT_SETUP_THREADS, DIRT_SETUP_MIN_BLOCKS) set
 {
     const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long total = (long long)d.B * d.F;
+    if (gid == 0) ws.header->tag = workspace_tag(vertices, faces, d.B, d.H, d.W, d.V, d.F);
     if (gid >= total) return;
     const int b = (int)(gid / d.F);
     const int f = (int)(gid - (long long)b * d.F);
@@ -48,6 +49,9 @@ __global__ void __launch_bounds__(DIRT_SETUP_THREADS, DIRT_SETUP_MIN_BLOCKS) set
         i[1] = make_uint4(0u, 0u, 0u, 0u);
         i[2] = make_uint4(__float_as_uint(1.0f), 0u, 0u, 0u);         // sC = 1, v0..v2 = 0
         i[3] = make_uint4(0u, 0u, 0u, 0u);
+        uint4* x = reinterpret_cast<uint4*>(ws.xy + gid);
+        x[0] = make_uint4(0u, 0u, 0u, 0u);
+        x[1] = make_uint4(0u, 0u, 0u, 0u);
         if (BIN) ws.tri_bin[gid] = make_uint2(0xFFFFFFFFu, 0xFFFFFFFFu);
     };
 
@@ -136,6 +140,9 @@ __global__ void __launch_bounds__(DIRT_SETUP_THREADS, DIRT_SETUP_MIN_BLOCKS) set
         union { TriInterp t; uint4 u[4]; } i; i.t = itp;
         uint4* dsti = reinterpret_cast<uint4*>(ws.itp + gid);
         dsti[0] = i.u[0]; dsti[1] = i.u[1]; dsti[2] = i.u[2]; dsti[3] = i.u[3];
+        float4* dstx = reinterpret_cast<float4*>(ws.xy + gid);
+        dstx[0] = make_float4(p[0][0], p[0][1], p[1][0], p[1][1]);
+        dstx[1] = make_float4(p[2][0], p[2][1], 0.f, 0.f);
     }
 
     // tile bounding box and the layout of the coverage record.
@@ -264,6 +271,8 @@ cudaError_t launch_setup_only(const float* vertices, const int32_t* faces, const
                               cudaStream_t stream, int* launches)
 {
     const long long total = (long long)d.B * d.F;
+    cudaError_t e;
+    if ((e = cudaMemsetAsync(ws.header, 0, sizeof(Header), stream)) != cudaSuccess) return e;
     if (total > 0) {
         setup_kernel<false><<<(unsigned)((total + DIRT_SETUP_THREADS - 1) / DIRT_SETUP_THREADS), DIRT_SETUP_THREADS, 0, stream>>>(vertices, faces, ws, d);
         ++*launches;

@@ -84,13 +84,25 @@ def rasterise_forward_raw(background, vertices, vertex_colors, faces, want_face_
                                                _stream_ptr(background.device))
     _lib.check(rc, 'Rasterise')
     if return_workspace:
+        ws._dirt_setup_of = _geometry_identity(vertices, faces, H, W)
         return pixels, face_ids, ws
     return pixels, face_ids
 
 
-def rasterise_backward_raw(vertices, faces, pixels, grad_pixels, face_ids=None, channel_groups=None, setup_workspace=None):
+def _geometry_identity(vertices, faces, H, W):
+    """What the setup records in a workspace were computed from: the tensors' storage AND their version counters
+    (an in-place update of the vertices makes the records stale; the C ABI's own tag cannot see that)."""
+    return (vertices.data_ptr(), vertices._version, tuple(vertices.shape), faces.data_ptr(), faces._version, tuple(faces.shape), H, W)
+
+
+def rasterise_backward_raw(vertices, faces, pixels, grad_pixels, face_ids=None, channel_groups=None, setup_workspace=None,
+                           shared_geometry=False, want_position=True, want_colour=True):
     """One call of dirt_rasterise_backward (the RasteriseGrad op, csrc/rasterise_grad_egl.cpp:33-53).
-    `setup_workspace`: the workspace tensor of the forward call on the same (vertices, faces), if still intact.
+    `setup_workspace`: the workspace tensor of the forward call on the same (vertices, faces); its setup records are
+    reused only if it still describes exactly these tensors (storage, version counters, sizes), otherwise they are
+    recomputed.  `shared_geometry`: accumulate the vertex gradients over the batch (DIRT_BWD_SHARED_GEOMETRY):
+    grad_vertices [V,4] and grad_vertex_colors [V,C] instead of [B,V,.].  want_position / want_colour = False skip
+    the position terms (grad_vertices comes back zero) / the colour terms (grad_vertex_colors zero, grad_background None).
     Returns (grad_background, grad_vertices, grad_vertex_colors)."""
     B, H, W, C = pixels.shape
     V, F = vertices.shape[1], faces.shape[1]
@@ -104,24 +116,37 @@ def rasterise_backward_raw(vertices, faces, pixels, grad_pixels, face_ids=None, 
     if faces.shape[0] != B or vertices.shape[0] != B:
         raise ValueError('RasteriseGrad expects all arguments to have same leading (batch) dimension')
     device = pixels.device
-    grad_background = torch.empty_like(pixels)
-    grad_vertices = torch.empty((B, V, 4), dtype=torch.float32, device=device)
-    grad_vertex_colors = torch.empty((B, V, C), dtype=torch.float32, device=device)
+    grad_background = torch.empty_like(pixels) if want_colour else None
+    lead = () if shared_geometry else (B,)
+    grad_vertices = torch.empty(lead + (V, 4), dtype=torch.float32, device=device)
+    grad_vertex_colors = torch.empty(lead + (V, C), dtype=torch.float32, device=device)
     if channel_groups is None:
         groups_ptr, n_groups = None, 0
     else:
         groups_arr = (ctypes.c_int * len(channel_groups))(*[int(g) for g in channel_groups])
         groups_ptr, n_groups = groups_arr, len(channel_groups)
     nbytes = int(_lib.lib().dirt_workspace_bytes(B, H, W, C, V, F))
-    reuse = int(setup_workspace is not None and face_ids is not None and setup_workspace.numel() >= nbytes)
+    reuse = int(setup_workspace is not None and face_ids is not None and setup_workspace.numel() >= nbytes and
+                getattr(setup_workspace, '_dirt_setup_of', None) == _geometry_identity(vertices, faces, H, W))
     ws = setup_workspace if reuse else _workspace(B, H, W, C, V, F, device)[0]
+    flags = ((_lib.BWD_SHARED_GEOMETRY if shared_geometry else 0) | (0 if want_position else _lib.BWD_SKIP_POSITION) |
+             (0 if want_colour else _lib.BWD_SKIP_COLOUR))
     with torch.cuda.device(device):
-        rc = _lib.lib().dirt_rasterise_backward(_ptr(vertices), _ptr(faces), _ptr(pixels), _ptr(grad_pixels), _ptr(face_ids),
-                                                _ptr(grad_background), _ptr(grad_vertices), _ptr(grad_vertex_colors),
-                                                B, H, W, C, V, F, groups_ptr, n_groups, reuse, _ptr(ws), nbytes,
-                                                _stream_ptr(device))
+        rc = _lib.lib().dirt_rasterise_backward_ex(
+            _ptr(vertices), _ptr(faces), _ptr(pixels), _ptr(grad_pixels), _ptr(face_ids),
+            _ptr(grad_background), _ptr(grad_vertices), _ptr(grad_vertex_colors),
+            B, H, W, C, V, F, groups_ptr, n_groups, reuse, flags, _ptr(ws), nbytes, _stream_ptr(device))
     _lib.check(rc, 'RasteriseGrad')
     return grad_background, grad_vertices, grad_vertex_colors
+
+
+def workspace_status(workspace, B, H, W, C, V, F):
+    """dirt_workspace_status: waits for the stream; raises if a backward call was handed a workspace that did not hold
+    the setup records it was promised (csrc/api.cu)."""
+    nbytes = int(_lib.lib().dirt_workspace_bytes(B, H, W, C, V, F))
+    with torch.cuda.device(workspace.device):
+        rc = _lib.lib().dirt_workspace_status(_ptr(workspace), nbytes, B, H, W, C, V, F, _stream_ptr(workspace.device))
+    _lib.check(rc, 'RasteriseGrad')
 
 
 def rasterise_visibility_raw(vertices, faces, height, width, want_gbuffer=True):
@@ -153,11 +178,16 @@ class _Rasterise(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, grad_pixels, _grad_face_ids):
+        want_background, want_vertices, want_colours = ctx.needs_input_grad[:3]
+        if not (want_background or want_vertices or want_colours):
+            return None, None, None, None, None
         vertices, faces, pixels, face_ids = ctx.saved_tensors
         grad_pixels = grad_pixels.contiguous().to(torch.float32)
         grad_background, grad_vertices, grad_vertex_colors = rasterise_backward_raw(
-            vertices, faces, pixels, grad_pixels, face_ids, ctx.channel_groups, ctx.setup_workspace)
-        return grad_background, grad_vertices, grad_vertex_colors, None, None  # None: wrt faces
+            vertices, faces, pixels, grad_pixels, face_ids, ctx.channel_groups, ctx.setup_workspace,
+            want_position=want_vertices, want_colour=want_background or want_colours)
+        return (grad_background if want_background else None, grad_vertices if want_vertices else None,
+                grad_vertex_colors if want_colours else None, None, None)  # None: wrt faces
 
 
 def _as_f32(x, device=None):
@@ -237,9 +267,12 @@ def rasterise_batch(background, vertices, vertex_colors, faces, height=None, wid
     return pixels
 
 
-def _rasterise_grad_multichannel(vertices, faces, pixels, d_loss_by_pixels, single_or_batch, face_ids=None):
+def _rasterise_grad_multichannel(vertices, faces, pixels, d_loss_by_pixels, single_or_batch, face_ids=None,
+                                 setup_workspace=None, want_position=True, want_colour=True):
     """dirt/rasterise_ops.py:132-177: RasteriseGrad over the greedy channel groups of `pixels`, summing
-    grad_vertices over groups and concatenating the others -- here one fused backward launch."""
+    grad_vertices over groups and concatenating the others -- here one fused backward call (no slicing, no copies).
+    Deferred shading uses only one half of each of its two calls (:206-237): want_position / want_colour = False
+    skip the other half inside the kernel."""
     assert single_or_batch in ['single', 'batch']
     if single_or_batch == 'single':
         vertices, faces, pixels, d_loss_by_pixels = vertices[None], faces[None], pixels[None], d_loss_by_pixels[None]
@@ -249,11 +282,20 @@ def _rasterise_grad_multichannel(vertices, faces, pixels, d_loss_by_pixels, sing
     groups = default_channel_groups(int(pixels.shape[3]))
     grad_background, grad_vertices, grad_vertex_colors = rasterise_backward_raw(
         vertices.contiguous(), faces.contiguous(), pixels.contiguous().to(torch.float32),
-        d_loss_by_pixels.contiguous().to(torch.float32), face_ids, groups)
+        d_loss_by_pixels.contiguous().to(torch.float32), face_ids, groups, setup_workspace,
+        want_position=want_position, want_colour=want_colour)
     if single_or_batch == 'single':
         return {'grad_vertices': grad_vertices[0], 'grad_vertex_colors': grad_vertex_colors[0],
-                'grad_background': grad_background[0]}
+                'grad_background': None if grad_background is None else grad_background[0]}
     return {'grad_vertices': grad_vertices, 'grad_vertex_colors': grad_vertex_colors, 'grad_background': grad_background}
+
+
+class _SetupHolder(object):
+    """Carries the forward call's workspace (per-face setup records, tile coverage flags) from the G-buffer node to the
+    vertex-gradient node of one deferred call without making it an autograd input."""
+
+    def __init__(self, workspace):
+        self.workspace = workspace
 
 
 class _RasteriseAttributes(torch.autograd.Function):
@@ -261,17 +303,24 @@ class _RasteriseAttributes(torch.autograd.Function):
     (the second RasteriseGrad call of dirt/rasterise_ops.py:233-237)."""
 
     @staticmethod
-    def forward(ctx, background, vertices, attributes, faces):
-        gbuffer, face_ids = rasterise_forward_raw(background, vertices, attributes, faces, want_face_ids=True)
+    def forward(ctx, background, vertices, attributes, faces, holder):
+        gbuffer, face_ids, ws = rasterise_forward_raw(background, vertices, attributes, faces, want_face_ids=True,
+                                                      return_workspace=True)
+        holder.workspace = ws
+        ctx.holder = holder
         ctx.save_for_backward(vertices, faces, gbuffer, face_ids)
         ctx.mark_non_differentiable(face_ids)
         return gbuffer, face_ids
 
     @staticmethod
     def backward(ctx, d_loss_by_gbuffer, _unused):
+        if not (ctx.needs_input_grad[0] or ctx.needs_input_grad[2]):
+            return None, None, None, None, None
         vertices, faces, gbuffer, face_ids = ctx.saved_tensors
-        grads = _rasterise_grad_multichannel(vertices, faces, gbuffer, d_loss_by_gbuffer, 'batch', face_ids)
-        return grads['grad_background'], None, grads['grad_vertex_colors'], None
+        # the vertex gradient of THIS call (filtering the G-buffer) is the one the reference discards (:233-237)
+        grads = _rasterise_grad_multichannel(vertices, faces, gbuffer, d_loss_by_gbuffer, 'batch', face_ids,
+                                             ctx.holder.workspace, want_position=False)
+        return grads['grad_background'], None, grads['grad_vertex_colors'], None, None
 
 
 class _InjectVertexGradient(torch.autograd.Function):
@@ -279,15 +328,19 @@ class _InjectVertexGradient(torch.autograd.Function):
     SHADED image (the first RasteriseGrad call of dirt/rasterise_ops.py:206-210)."""
 
     @staticmethod
-    def forward(ctx, pixels, vertices, faces, face_ids):
+    def forward(ctx, pixels, vertices, faces, face_ids, holder):
+        ctx.holder = holder
         ctx.save_for_backward(pixels.detach(), vertices, faces, face_ids)
         return pixels.view_as(pixels)
 
     @staticmethod
     def backward(ctx, d_loss_by_pixels):
+        if not ctx.needs_input_grad[1]:
+            return d_loss_by_pixels, None, None, None, None
         pixels, vertices, faces, face_ids = ctx.saved_tensors
-        d_loss_by_vertices = _rasterise_grad_multichannel(vertices, faces, pixels, d_loss_by_pixels, 'batch', face_ids)['grad_vertices']
-        return d_loss_by_pixels, d_loss_by_vertices, None, None
+        d_loss_by_vertices = _rasterise_grad_multichannel(vertices, faces, pixels, d_loss_by_pixels, 'batch', face_ids,
+                                                          ctx.holder.workspace, want_colour=False)['grad_vertices']
+        return d_loss_by_pixels, d_loss_by_vertices, None, None, None
 
 
 def _rasterise_deferred_internal(background, vertices, attributes, faces, shader_fn, shader_additional_inputs, single_or_batch, name):
@@ -308,14 +361,15 @@ def _rasterise_deferred_internal(background, vertices, attributes, faces, shader
                   int(background.shape[3]))
     _require_cuda(background, vertices, attributes, faces)
     background, vertices, attributes, faces = background.contiguous(), vertices.contiguous(), attributes.contiguous(), faces.contiguous()
-    gbuffer, face_ids = _RasteriseAttributes.apply(background, vertices, attributes, faces)
+    holder = _SetupHolder(None)
+    gbuffer, face_ids = _RasteriseAttributes.apply(background, vertices, attributes, faces, holder)
     if single_or_batch == 'single':
         pixels = shader_fn(gbuffer[0], *shader_additional_inputs)[None]
     else:
         pixels = shader_fn(gbuffer, *shader_additional_inputs)
     if pixels.dim() != 4 or pixels.shape[:3] != gbuffer.shape[:3]:
         raise ValueError('shader_fn must return pixels of shape [height, width, channels] per image')
-    pixels = _InjectVertexGradient.apply(pixels.to(torch.float32), vertices, faces, face_ids)
+    pixels = _InjectVertexGradient.apply(pixels.to(torch.float32), vertices, faces, face_ids, holder)
     return pixels[0] if single_or_batch == 'single' else pixels
 
 

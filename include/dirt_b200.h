@@ -48,7 +48,8 @@ enum {
     DIRT_ERR_BAD_CHANNEL_GROUPS = -4, /* groups must be 1 or 3 wide and sum to C (rasterise_ops.py:80-108) */
     DIRT_ERR_TOO_MANY_VERTICES = -5,  /* V > 2^24, csrc/rasterise_grad_egl.cpp:399-405 */
     DIRT_ERR_CUDA = -6,               /* a CUDA runtime call or kernel launch failed */
-    DIRT_ERR_MISALIGNED = -7          /* a pointer is not aligned as required (workspace: 256 B, tensors: 4 B) */
+    DIRT_ERR_MISALIGNED = -7,         /* a pointer is not aligned as required (workspace: 256 B, tensors: 4 B) */
+    DIRT_ERR_STALE_WORKSPACE = -8     /* dirt_workspace_status: a backward call was promised setup records that were not there */
 };
 
 /* Human-readable text for an error code (static storage, never NULL). */
@@ -82,6 +83,11 @@ int dirt_rasterise_forward(const float* background, const float* vertices,
  * workspace_holds_setup != 0 promises that `workspace` is the buffer a preceding dirt_rasterise_forward /
  * dirt_rasterise_visibility call on the SAME (vertices, faces, H, W) filled and that nothing has written to it
  * since: the per-face setup records are then reused instead of recomputed (only meaningful with face_ids).
+ * The promise is checked on the device: the setup pass leaves a tag (hash of the vertices / faces pointers and the
+ * sizes) in the workspace; a backward call that finds another tag sets an error flag in the workspace (reported by
+ * dirt_workspace_status) and writes NaN into grad_vertices[0] instead of returning plausible numbers.  What the tag
+ * cannot see is an in-place change of the vertex VALUES between the two calls; the Python layer covers that with
+ * the tensors' version counters.
  * grad_vertices / grad_vertex_colors are zeroed by the library before accumulation;
  * grad_background is written exactly once per pixel. */
 int dirt_rasterise_backward(const float* vertices, const int32_t* faces,
@@ -91,6 +97,33 @@ int dirt_rasterise_backward(const float* vertices, const int32_t* faces,
                             int B, int H, int W, int C, int V, int F,
                             const int* channel_groups, int n_groups, int workspace_holds_setup,
                             void* workspace, size_t workspace_bytes, void* cuda_stream);
+
+/* dirt_rasterise_backward with options (flags = 0 is dirt_rasterise_backward itself):
+ *  DIRT_BWD_SHARED_GEOMETRY  the vertex gradients are ACCUMULATED OVER THE BATCH: grad_vertices is [V,4] and
+ *      grad_vertex_colors [V,C], sum_b of the per-item results -- the gradient of geometry / colours that are parameters
+ *      shared by the batch (the reference leaves that sum to TensorFlow's broadcast gradient).  Saves the
+ *      [B,V,.] buffers, their memsets and the reduction pass; it is the buffer a multi-GPU job all-reduces.
+ *  DIRT_BWD_SKIP_POSITION    grad_vertices is not computed (left zero): no Scharr filter, no dilation, `pixels` is not read.
+ *  DIRT_BWD_SKIP_COLOUR      grad_vertex_colors is not computed (left zero) and grad_background is not written.
+ *  The two SKIP flags serve deferred shading, whose gradient is two RasteriseGrad calls of which only one output each
+ *  is used (dirt/rasterise_ops.py:206-237: vertices from the shaded pixels, attributes / background from the G-buffer). */
+enum {
+    DIRT_BWD_SHARED_GEOMETRY = 1,
+    DIRT_BWD_SKIP_POSITION = 2,
+    DIRT_BWD_SKIP_COLOUR = 4
+};
+int dirt_rasterise_backward_ex(const float* vertices, const int32_t* faces,
+                               const float* pixels, const float* grad_pixels,
+                               const int32_t* face_ids,
+                               float* grad_background, float* grad_vertices, float* grad_vertex_colors,
+                               int B, int H, int W, int C, int V, int F,
+                               const int* channel_groups, int n_groups, int workspace_holds_setup, int flags,
+                               void* workspace, size_t workspace_bytes, void* cuda_stream);
+
+/* Waits for the stream and reports whether a backward call found the workspace not to hold the setup records it was
+ * promised (DIRT_ERR_STALE_WORKSPACE), else DIRT_OK.  The only entry point that synchronises the host. */
+int dirt_workspace_status(const void* workspace, size_t workspace_bytes,
+                          int B, int H, int W, int C, int V, int F, void* cuda_stream);
 
 /* Debug / parity: the visibility G-buffer alone (either output may be NULL). */
 int dirt_rasterise_visibility(const float* vertices, const int32_t* faces,

@@ -294,3 +294,165 @@ def test_full_size_properties(cuda_lib):
         assert float((b12[k] - ref).abs().max()) <= 2e-4 * float(ref.abs().max())
     assert torch.equal(b1[0][~cov], g1[~cov]) and float(b1[0][cov].abs().max()) == 0.0
     assert float(b1[1][..., 2].abs().max()) == 0.0
+
+
+# ---- round 2: accumulation over the batch, partial gradients, workspace validation, full sizes -------------------
+
+def test_shared_geometry_accumulates_over_the_batch(cuda_lib, oracle):
+    # DIRT_BWD_SHARED_GEOMETRY: [V,4] / [V,C] outputs equal the per-item gradients summed over the batch
+    import torch
+    from dirt_b200 import rasterise_ops as ops
+    for s in (scenes.config3(batch=5, width=160, height=128, level=3, background='uniform'),
+              scenes.config4(batch=4, width=128, height=96, level=2)):
+        t = _cuda(s)
+        pixels, ids, ws = ops.rasterise_forward_raw(t['background'], t['vertices'], t['vertex_colors'], t['faces'], True, True)
+        gp = torch.from_numpy(np.random.default_rng(9).standard_normal(tuple(pixels.shape)).astype(np.float32)).cuda()
+        gb, gv, gc = ops.rasterise_backward_raw(t['vertices'], t['faces'], pixels, gp, ids, None, ws, shared_geometry=True)
+        assert tuple(gv.shape) == tuple(s['vertices'].shape[1:]) and tuple(gc.shape) == tuple(s['vertex_colors'].shape[1:])
+        gb_o, gv_o, gc_o = oracle.backward(s['vertices'], s['faces'], pixels.cpu().numpy(), gp.cpu().numpy())
+        np.testing.assert_array_equal(gb.cpu().numpy(), gb_o)
+        for name, got, want in (('grad_vertices', gv, gv_o.astype(np.float64).sum(0)), ('grad_vertex_colors', gc, gc_o.astype(np.float64).sum(0))):
+            ok, ratio = rel_close(got.cpu().numpy(), want)
+            assert ok, 'shared %s off by %.2fx the tolerance' % (name, ratio)
+
+
+@pytest.mark.parametrize('channels', [1, 3, 4, 7])
+def test_partial_gradients(cuda_lib, oracle, channels):
+    # DIRT_BWD_SKIP_POSITION / DIRT_BWD_SKIP_COLOUR: each half equals the corresponding outputs of the full call
+    import torch
+    from dirt_b200 import rasterise_ops as ops
+    s = scenes.random_soup(batch=2, width=61, height=45, n_faces=70, channels=channels, seed=4)
+    t = _cuda(s)
+    pixels, ids = ops.rasterise_forward_raw(t['background'], t['vertices'], t['vertex_colors'], t['faces'])
+    gp = torch.from_numpy(np.random.default_rng(2).standard_normal(tuple(pixels.shape)).astype(np.float32)).cuda()
+    gb_o, gv_o, gc_o = oracle.backward(s['vertices'], s['faces'], pixels.cpu().numpy(), gp.cpu().numpy())
+    gb, gv, gc = ops.rasterise_backward_raw(t['vertices'], t['faces'], pixels, gp, ids, want_position=False)
+    np.testing.assert_array_equal(gb.cpu().numpy(), gb_o)
+    assert rel_close(gc.cpu().numpy(), gc_o)[0] and float(gv.abs().max()) == 0.0
+    gb, gv, gc = ops.rasterise_backward_raw(t['vertices'], t['faces'], pixels, gp, ids, want_colour=False)
+    assert gb is None and float(gc.abs().max()) == 0.0
+    ok, ratio = rel_close(gv.cpu().numpy(), gv_o)
+    assert ok, 'position-only grad_vertices off by %.2fx the tolerance' % ratio
+
+
+def test_stale_workspace_is_detected(cuda_lib, oracle):
+    # workspace_holds_setup is a checked promise: a workspace filled for OTHER geometry raises the device-side flag
+    # and poisons grad_vertices; the Python layer never makes the promise for a workspace that does not match
+    import ctypes
+    import torch
+    from dirt_b200 import rasterise_ops as ops, _lib
+    s = scenes.config3(batch=2, width=96, height=64, level=2, background='uniform')
+    t = _cuda(s)
+    other = {k: v.clone() for k, v in t.items()}
+    other['vertices'][..., 0] += 0.05
+    pixels, ids, ws = ops.rasterise_forward_raw(t['background'], t['vertices'], t['vertex_colors'], t['faces'], True, True)
+    _, _, ws_other = ops.rasterise_forward_raw(other['background'], other['vertices'], other['vertex_colors'], other['faces'], True, True)
+    gp = torch.randn_like(pixels)
+    B, H, W, C = pixels.shape
+    V, F = t['vertices'].shape[1], t['faces'].shape[1]
+    want = oracle.backward(s['vertices'], s['faces'], pixels.cpu().numpy(), gp.cpu().numpy())
+    # (a) Python layer: the foreign workspace is not reused, the result is right
+    got = ops.rasterise_backward_raw(t['vertices'], t['faces'], pixels, gp, ids, None, ws_other)
+    assert rel_close(got[1].cpu().numpy(), want[1])[0]
+    ops.workspace_status(ws_other, B, H, W, C, V, F)   # no flag raised
+    # an in-place update of the vertices invalidates the matching workspace as well (version counter)
+    t['vertices'].add_(0.0)
+    got = ops.rasterise_backward_raw(t['vertices'], t['faces'], pixels, gp, ids, None, ws)
+    assert rel_close(got[1].cpu().numpy(), want[1])[0]
+    # (b) C ABI: make the false promise directly
+    L = _lib.lib()
+    gb = torch.empty_like(pixels); gv = torch.empty((B, V, 4), device='cuda'); gc = torch.empty((B, V, C), device='cuda')
+    p = lambda x: ctypes.c_void_p(x.data_ptr())
+    nbytes = int(L.dirt_workspace_bytes(B, H, W, C, V, F))
+    stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    rc = L.dirt_rasterise_backward(p(t['vertices']), p(t['faces']), p(pixels), p(gp), p(ids), p(gb), p(gv), p(gc),
+                                   B, H, W, C, V, F, None, 0, 1, p(ws_other), nbytes, stream)
+    assert rc == 0
+    torch.cuda.synchronize()
+    assert bool(torch.isnan(gv.flatten()[0]))
+    with pytest.raises(RuntimeError):
+        ops.workspace_status(ws_other, B, H, W, C, V, F)
+    # the matching workspace passes
+    rc = L.dirt_rasterise_backward(p(t['vertices']), p(t['faces']), p(pixels), p(gp), p(ids), p(gb), p(gv), p(gc),
+                                   B, H, W, C, V, F, None, 0, 1, p(ws), nbytes, stream)
+    assert rc == 0
+    ops.workspace_status(ws, B, H, W, C, V, F)
+    assert rel_close(gv.cpu().numpy(), want[1])[0]
+
+
+@pytest.mark.parametrize('name,kwargs', [
+    ('config3', dict(batch=2, width=512, height=512, background='uniform')),       # the benched workload's frame and mesh
+    ('config4', dict(batch=2, width=512, height=512)),
+    ('config5', dict(batch=1, width=1024, height=1024)),                           # 49 728 faces, pole slivers
+    ('cube_scene', dict(width=640, height=480)),                                   # samples/simple.py: 12 large faces
+])
+def test_full_size_configs_match_oracle(cuda_lib, oracle, name, kwargs):
+    _check_scene(oracle, getattr(scenes, name)(**kwargs), label=name + '-full')
+
+
+def test_direct_and_deferred_agree_for_a_linear_shader(cuda_lib):
+    # tests/deferred_grad_test.py:168-219 renders direct (Gouraud) and deferred gradients side by side.  For a shader that
+    # is LINEAR in the attributes the two recipes are the same function, so pixels and every gradient must agree:
+    # vertices (filtering the shaded image), attributes / background (through shader_fn) and the shader's own inputs.
+    import torch
+    import dirt_b200 as dirt
+    s = scenes.bent_square_scene(48, 40, channels=6, seed=2)
+    t = _cuda(s)
+    gp = torch.from_numpy(np.random.default_rng(4).standard_normal((48 * 40 * 3,)).astype(np.float32)).cuda().reshape(1, 40, 48, 3)
+
+    def run(deferred):
+        leaves = {k: t[k].clone().requires_grad_(True) for k in ('background', 'vertices', 'vertex_colors')}
+        gain = torch.tensor([0.7, 1.3, 0.4], device='cuda', requires_grad=True)
+        shade = lambda a, k: a[..., :3] * k + 0.5 * a[..., 3:6]
+        if deferred:
+            pixels = dirt.rasterise_batch_deferred(leaves['background'], leaves['vertices'], leaves['vertex_colors'], t['faces'],
+                                                   shade, [gain])
+        else:
+            pixels = dirt.rasterise_batch(shade(leaves['background'], gain), leaves['vertices'], shade(leaves['vertex_colors'], gain),
+                                          t['faces'])
+        (pixels * gp).sum().backward()
+        return pixels.detach(), [leaves[k].grad for k in ('background', 'vertices', 'vertex_colors')] + [gain.grad]
+
+    pix_a, grads_a = run(False)
+    pix_b, grads_b = run(True)
+    assert rel_close(pix_b.cpu().numpy(), pix_a.cpu().numpy())[0]
+    for name, a, b in zip(('background', 'vertices', 'attributes', 'gain'), grads_a, grads_b):
+        ok, ratio = rel_close(b.cpu().numpy(), a.cpu().numpy(), rel=2e-4)
+        assert ok, 'deferred vs direct: grad %s off by %.2fx the tolerance' % (name, ratio)
+
+
+def test_pixel_jacobians_of_the_cylinder(cuda_lib, oracle):
+    # tests/rasterise_tests.py:108-131 evaluates d pixel / d (translation, rotation, background, colour) one pixel at a
+    # time.  Same recipe through the public API, compared with the oracle chained through the same torch transform.
+    import torch
+    import dirt_b200 as dirt
+    s = scenes.cylinder_scene()
+    H, W = s['background'].shape[1:3]
+    base = torch.from_numpy(s['vertices'][0]).cuda()
+
+    def clip_vertices(translation):
+        # a clip-space shift stands in for the scene's translation parameter: x, y scale with w like a view-space shift does
+        return base + torch.stack([translation[0] * base[:, 3], translation[1] * base[:, 3], translation[2] * 0 * base[:, 3],
+                                   torch.zeros_like(base[:, 3])], dim=1)
+
+    pixels_o = oracle.forward(**s)
+    rng = np.random.default_rng(0)
+    ids = oracle.visibility(s['vertices'], s['faces'], H, W)[0][0]
+    edge = np.argwhere((ids >= 0) & ((np.roll(ids, 1, 1) < 0) | (np.roll(ids, -1, 0) < 0)))
+    picks = [tuple(edge[i]) for i in rng.choice(len(edge), size=6, replace=False)] + [(H // 2, W // 2), (2, 3)]
+    for (y, x) in picks:
+        for c in (0, 2):
+            translation = torch.zeros(3, device='cuda', requires_grad=True)
+            bg = torch.from_numpy(s['background'][0]).cuda().requires_grad_(True)
+            col = torch.from_numpy(s['vertex_colors'][0]).cuda().requires_grad_(True)
+            pixels = dirt.rasterise(bg, clip_vertices(translation), col, torch.from_numpy(s['faces'][0]).cuda())
+            pixels[y, x, c].backward()
+            indicator = np.zeros_like(pixels_o); indicator[0, y, x, c] = 1.0
+            gb_o, gv_o, gc_o = oracle.backward(s['vertices'], s['faces'], pixels_o, indicator)
+            t_cpu = torch.zeros(3, requires_grad=True)
+            b_cpu = base.cpu()
+            v_cpu = b_cpu + torch.stack([t_cpu[0] * b_cpu[:, 3], t_cpu[1] * b_cpu[:, 3], t_cpu[2] * 0 * b_cpu[:, 3], torch.zeros_like(b_cpu[:, 3])], dim=1)
+            (v_cpu * torch.from_numpy(gv_o[0])).sum().backward()
+            np.testing.assert_allclose(translation.grad.cpu().numpy(), t_cpu.grad.numpy(), rtol=1e-4, atol=1e-6 * float(np.abs(gv_o).max() + 1))
+            np.testing.assert_array_equal(bg.grad.cpu().numpy(), gb_o[0])
+            assert rel_close(col.grad.cpu().numpy(), gc_o[0])[0]
