@@ -6,9 +6,10 @@
 // and the output written directly in the [B,H,W,C] tensors, top row first.
 //
 // A pair of tiles with nothing binned to either is copied in one go, both tiles' loads in flight (such a tile is pure
-// latency: range -> background -> store).  Otherwise, per tile, the binned face list (KIND_SMALL faces, int32 arithmetic
-// only) and the image's large list (KIND_LARGE: int64 tile-origin move; KIND_HARD: homogeneous fp64) are consumed in
-// chunks of 32:
+// latency: count -> background -> store).  Otherwise, per tile, the tile's bin (KIND_SMALL faces, int32 arithmetic
+// only; its place is a function of the tile index, so count and references arrive in one hop), the image's overflow
+// list if the bin was full, and the image's large list (KIND_LARGE: int64 tile-origin move; KIND_HARD: homogeneous
+// fp64) are consumed in chunks of 32:
 //   lane phase  : one face per lane -- load its 64-B coverage record, move the three edge functions
 //                 to the tile origin, reject faces whose edge functions are negative on the whole
 //                 tile, bound the face's nearest depth key over the tile, park survivors in shared
@@ -105,9 +106,10 @@ __device__ __noinline__ uint4 hard_face_keys(const float* __restrict__ verts, co
     return make_uint4(keys[0], keys[1], keys[2], keys[3]);
 }
 
-// Consume one face list for this warp's tile.  SMALL: the list holds KIND_SMALL faces only.
-template <bool SMALL>
-__device__ __forceinline__ void consume_list(const int* __restrict__ list, int count, const TriCov* __restrict__ cov_b,
+// Consume one face list for this warp's tile.  SMALL: the list holds KIND_SMALL faces only.  FILTER: the list holds
+// (tile, face) pairs of the whole image (the overflow list) and only those of tile `want_tile` count.
+template <bool SMALL, bool FILTER>
+__device__ __forceinline__ void consume_list(const int* __restrict__ list, int count, int want_tile, const TriCov* __restrict__ cov_b,
                                              const TriInterp* __restrict__ itp_b, const float* __restrict__ verts,
                                              Slot* slots, int lane, int tcol0, int trow0, int H, int W, Quad& quad,
                                              uint32_t& tile_max)
@@ -117,7 +119,16 @@ __device__ __forceinline__ void consume_list(const int* __restrict__ list, int c
 
     for (int base = 0; base < count; base += 32) {
         const int i = base + lane;
-        const int f = (i < count) ? __ldg(&list[i]) : -1;
+        int f = -1;
+        if (i < count) {
+            if (FILTER) {
+                const int2 e = __ldg(reinterpret_cast<const int2*>(list) + i);
+                f = (e.x == want_tile) ? e.y : -1;
+            } else {
+                f = __ldg(&list[i]);
+            }
+        }
+        if (FILTER && !__any_sync(0xffffffffu, f >= 0)) continue;
         uint32_t order = 0xFFFFFFFFu;   // (nearest possible depth key << 5) | lane; 0xFFFFFFFF: not a candidate
         if (f >= 0) {
             const TriCov c = load_cov(cov_b + f);
@@ -268,9 +279,9 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, DIRT_RASTER_MIN_BLOCKS) 
     // Two neighbouring tiles with nothing binned to either (most of a frame): one pass with both tiles' loads in
     // flight -- an empty tile is pure latency (range -> background -> store), so this doubles the bytes per resident warp.
     if (MODE == 0 && (CT == 4 || CT == 3) && txb + 1 < d.tiles_x && (txb + 2) * TILE_W <= d.W && trow0 + TILE_H <= d.H) {
-        const int2* rp = ws.tile_range + (size_t)b * d.tiles + ty * d.tiles_x + txb;
-        const int2 ra = rp[0], rb = rp[1];
-        if (ra.y == 0 && rb.y == 0 && ws.large_count[b] == 0) {
+        const int* cp = ws.tile_count + (size_t)b * d.tiles + ty * d.tiles_x + txb;
+        const int cnt_a = cp[0], cnt_b = cp[1];
+        if (cnt_a == 0 && cnt_b == 0 && ws.large_count[b] == 0) {
             const int col0 = txb * TILE_W + (lane & 7) * 2, row0 = trow0 + (lane >> 3) * 2;
             const size_t p00 = ((size_t)b * d.H + row0) * d.W + col0;
             if (CT == 4) {
@@ -320,7 +331,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, DIRT_RASTER_MIN_BLOCKS) 
             asm volatile("prefetch.global.L2 [%0];" ::"l"(background + (((size_t)b * d.H + r) * d.W + c) * 4));
     }
 #endif
-    const int2 range = ws.tile_range[(size_t)b * d.tiles + t];
+    const int nbin = ws.tile_count[(size_t)b * d.tiles + t];
     const int nlarge = ws.large_count[b];
     const int col0 = tcol0 + (lane & 7) * 2, row0 = trow0 + (lane >> 3) * 2;
     const size_t p00 = ((size_t)b * d.H + row0) * d.W + col0;   // pixel (row0, col0); the quad is p00 + {0, 1, W, W+1}
@@ -328,7 +339,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, DIRT_RASTER_MIN_BLOCKS) 
     const int C = (CT > 0) ? CT : d.C;
 
     // ---- nothing binned to this tile: the background passes through ----------------------------------------
-    if (range.y == 0 && nlarge == 0) {
+    if (nbin == 0 && nlarge == 0) {
         if (MODE == 0 && CT == 3 && whole) {
             const float2* src = reinterpret_cast<const float2*>(background);
             float2* dst = reinterpret_cast<float2*>(pixels);
@@ -366,12 +377,16 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, DIRT_RASTER_MIN_BLOCKS) 
 #pragma unroll
     for (int i = 0; i < 4; ++i) quad.best[i] = pack(KEY_EMPTY, 0);
     uint32_t tile_max = KEY_EMPTY;
-    if (range.y > 0)
-        consume_list<true>(ws.refs + range.x, range.y, cov_b, itp_b, verts, slots_all[warp], lane, tcol0, trow0, d.H, d.W,
-                           quad, tile_max);
+    if (nbin > 0)
+        consume_list<true, false>(ws.bins + ((size_t)b * d.tiles + t) * BIN_CAP, min(nbin, BIN_CAP), 0, cov_b, itp_b, verts,
+                                  slots_all[warp], lane, tcol0, trow0, d.H, d.W, quad, tile_max);
+    if (nbin > BIN_CAP)   // the bin was full: this tile's share of the image's overflow list
+        consume_list<true, true>(reinterpret_cast<const int*>(ws.ovf + (size_t)b * OVF_PER_FACE * d.F),
+                                 min(ws.ovf_count[b], OVF_PER_FACE * d.F), t, cov_b, itp_b, verts, slots_all[warp], lane,
+                                 tcol0, trow0, d.H, d.W, quad, tile_max);
     if (nlarge > 0)
-        consume_list<false>(ws.large_list + (size_t)b * d.F, nlarge, cov_b, itp_b, verts, slots_all[warp], lane, tcol0,
-                            trow0, d.H, d.W, quad, tile_max);
+        consume_list<false, false>(ws.large_list + (size_t)b * d.F, nlarge, 0, cov_b, itp_b, verts, slots_all[warp], lane, tcol0,
+                                   trow0, d.H, d.W, quad, tile_max);
 
     // tile coverage flags for the backward pass: a tile that shows any face marks itself and its 8 neighbours
     // (the backward pass reaches one pixel beyond its own tile)

@@ -5,12 +5,11 @@
 // upload_vertices (csrc/rasterise_grad_egl.cu:12-34).
 //
 //   setup_kernel : one thread per (image, face): S1-S6 of the visibility specification ->
-//                  TriCov + TriInterp records, tile bounding box, per-tile reference counts
-//                  (faces spanning <= SMALL_TILE_LIMIT tiles) or the per-image large list.
-//   scan_kernel  : turns per-tile counts into (offset,count) ranges in the reference pool
-//                  (block-local exclusive scan + one atomic per block; list order is irrelevant
-//                  because visibility is the minimum of (depth key, face index)).
-//   fill_kernel  : one thread per (image, face): writes the face index into each tile's range.
+//                  TriCov + TriInterp + TriXY records, and -- in the same pass -- binning: the face is appended to the
+//                  fixed-capacity bin of every tile its bounding box touches (faces spanning <= SMALL_TILE_LIMIT
+//                  tiles; position = atomicAdd on the tile's count, overflow -> the image's overflow list) or to
+//                  the per-image large list.  The order inside a bin is irrelevant: visibility is the minimum of
+//                  (depth key, face index).  No scan, no second pass.
 #include "common.cuh"
 
 namespace dirt {
@@ -52,7 +51,6 @@ __global__ void __launch_bounds__(DIRT_SETUP_THREADS, DIRT_SETUP_MIN_BLOCKS) set
         uint4* x = reinterpret_cast<uint4*>(ws.xy + gid);
         x[0] = make_uint4(0u, 0u, 0u, 0u);
         x[1] = make_uint4(0u, 0u, 0u, 0u);
-        if (BIN) ws.tri_bin[gid] = make_uint2(0xFFFFFFFFu, 0xFFFFFFFFu);
     };
 
     int32_t vid[3];
@@ -178,90 +176,44 @@ __global__ void __launch_bounds__(DIRT_SETUP_THREADS, DIRT_SETUP_MIN_BLOCKS) set
     }
     if (!BIN) return;
 
-    if (small) {
-        ws.tri_bin[gid] = make_uint2((uint32_t)tx0 | ((uint32_t)ty0 << 16), (uint32_t)tx1 | ((uint32_t)ty1 << 16));
-        int* counts = ws.tile_count + (size_t)b * d.tiles;
-        for (int ty = ty0; ty <= ty1; ++ty)
-            for (int tx = tx0; tx <= tx1; ++tx) atomicAdd(&counts[ty * d.tiles_x + tx], 1);
-    } else {
-        ws.tri_bin[gid] = make_uint2(0xFFFFFFFFu, 0xFFFFFFFFu);
+    const auto to_large_list = [&]() {
         const int pos = atomicAdd(&ws.large_count[b], 1);
         ws.large_list[(size_t)b * d.F + pos] = f;
+    };
+    if (small) {
+        int* counts = ws.tile_count + (size_t)b * d.tiles;
+        for (int ty = ty0; ty <= ty1; ++ty)
+            for (int tx = tx0; tx <= tx1; ++tx) {
+                const int t = ty * d.tiles_x + tx;
+                const int pos = atomicAdd(&counts[t], 1);
+                if (pos < BIN_CAP) {
+                    ws.bins[((size_t)b * d.tiles + t) * BIN_CAP + pos] = f;
+                } else {
+                    // the tile's bin is full: the image's overflow list, and if that is full as well the large list
+                    // (a face that sits in both a bin and the large list is tested twice, which cannot change a minimum)
+                    const int q = atomicAdd(&ws.ovf_count[b], 1);
+                    if (q < OVF_PER_FACE * d.F) ws.ovf[(size_t)b * OVF_PER_FACE * d.F + q] = make_int2(t, f);
+                    else {
+                        // one byte per face, claimed with an atomic OR on the word holding it
+                        unsigned int* word = reinterpret_cast<unsigned int*>(ws.face_in_large) + (gid >> 2);
+                        const unsigned int bit = 1u << (8 * (unsigned)(gid & 3));
+                        if ((atomicOr(word, bit) & bit) == 0u) to_large_list();
+                    }
+                }
+            }
+    } else {
+        to_large_list();
     }
-}
-
-// per-tile counts -> (offset,count); zeroes the count so fill_kernel can reuse it as a cursor
-__global__ void __launch_bounds__(1024) scan_kernel(Workspace ws, long long total_tiles)
-{
-    __shared__ int warp_sums[32];
-    __shared__ int block_base;
-    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    int count = 0;
-    if (gid < total_tiles) count = ws.tile_count[gid];
-    int incl = count;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const int v = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += v;
-    }
-    if (lane == 31) warp_sums[warp] = incl;
-    __syncthreads();
-    if (warp == 0) {
-        int w = warp_sums[lane];
-        int wi = w;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int v = __shfl_up_sync(0xffffffffu, wi, o);
-            if (lane >= o) wi += v;
-        }
-        warp_sums[lane] = wi - w;  // exclusive
-        if (lane == 31) block_base = atomicAdd(ws.pool_cursor, wi);
-    }
-    __syncthreads();
-    if (gid < total_tiles) {
-        const int offset = block_base + warp_sums[warp] + incl - count;
-        ws.tile_range[gid] = make_int2(offset, count);
-        ws.tile_count[gid] = 0;
-    }
-}
-
-__global__ void __launch_bounds__(256) fill_kernel(Workspace ws, Dims d)
-{
-    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long total = (long long)d.B * d.F;
-    if (gid >= total) return;
-    const uint2 bin = ws.tri_bin[gid];
-    if (bin.x == 0xFFFFFFFFu) return;
-    const int b = (int)(gid / d.F);
-    const int f = (int)(gid - (long long)b * d.F);
-    const int tx0 = bin.x & 0xFFFF, ty0 = bin.x >> 16, tx1 = bin.y & 0xFFFF, ty1 = bin.y >> 16;
-    const size_t tbase = (size_t)b * d.tiles;
-    for (int ty = ty0; ty <= ty1; ++ty)
-        for (int tx = tx0; tx <= tx1; ++tx) {
-            const size_t t = tbase + (size_t)ty * d.tiles_x + tx;
-            const int pos = atomicAdd(&ws.tile_count[t], 1);
-            ws.refs[ws.tile_range[t].x + pos] = f;
-        }
 }
 
 cudaError_t launch_setup_and_bin(const float* vertices, const int32_t* faces, const Workspace& ws, const Dims& d,
                                  cudaStream_t stream, int* launches)
 {
     const long long total = (long long)d.B * d.F;
-    const long long total_tiles = (long long)d.B * d.tiles;
     cudaError_t e;
     if ((e = cudaMemsetAsync(ws.tile_count, 0, ws.zero_bytes, stream)) != cudaSuccess) return e;
     if (total > 0) {
         setup_kernel<true><<<(unsigned)((total + DIRT_SETUP_THREADS - 1) / DIRT_SETUP_THREADS), DIRT_SETUP_THREADS, 0, stream>>>(vertices, faces, ws, d);
-        ++*launches;
-    }
-    if (total_tiles > 0) {
-        scan_kernel<<<(unsigned)((total_tiles + 1023) / 1024), 1024, 0, stream>>>(ws, total_tiles);
-        ++*launches;
-    }
-    if (total > 0) {
-        fill_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(ws, d);
         ++*launches;
     }
     return cudaGetLastError();
