@@ -27,6 +27,10 @@ import time
 
 import numpy as np
 
+# stable placement of the OpenMP threads of the CPU legs (read by libgomp when oracle/libdirt_oracle.so is loaded)
+os.environ.setdefault('OMP_PROC_BIND', 'true')
+os.environ.setdefault('OMP_PLACES', 'threads')
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
@@ -345,6 +349,32 @@ def check_against_oracle(prep, scene, images=1):
     return res
 
 
+def numpy_baselines(scene, grad_pixels, threads, one_process_images=2, budget_s=20.0):
+    """The reference-style numpy path (oracle/numpy_raster.py: coverage on a meshgrid of pixel centres, as
+    tests/square_test.py:11-17 does for its square) fwd+bwd: (i) one process, (ii) a multiprocessing pool over the
+    images on every host thread.  Bounded samples of the same workload."""
+    from oracle import numpy_raster as npr
+    B, H, W = scene['background'].shape[:3]
+    out = {}
+    n1 = min(one_process_images, B)
+    sub = {k: v[:n1] for k, v in scene.items()}
+    t0 = time.perf_counter()
+    npr.forward_backward_batch(sub, grad_pixels[:n1], processes=1)
+    dt1 = time.perf_counter() - t0
+    out['numpy_1_process'] = {'value': n1 * H * W / dt1 / 1e6, 'unit': UNIT, 'cores': 1,
+                              'sample': '%d images, %.1f s' % (n1, dt1)}
+    # pool: as many images as one round of all workers renders within the budget
+    procs = max(1, threads)
+    nmp = max(1, min(B, int(procs * max(1.0, budget_s / max(dt1 / n1, 1e-3) / 4.0))))
+    sub = {k: v[:nmp] for k, v in scene.items()}
+    t0 = time.perf_counter()
+    npr.forward_backward_batch(sub, grad_pixels[:nmp], processes=min(procs, nmp))
+    dtm = time.perf_counter() - t0
+    out['numpy_multiprocessing'] = {'value': nmp * H * W / dtm / 1e6, 'unit': UNIT, 'cores': min(procs, nmp),
+                                    'sample': '%d images over %d processes, %.1f s (pool start-up included)' % (nmp, min(procs, nmp), dtm)}
+    return out
+
+
 def cpu_baseline(scene, grad_pixels, sample_images, threads=None, min_seconds=10.0):
     """fwd+bwd of the CPU oracle (a port of the reference path) on `sample_images` images of the workload,
     repeated until at least `min_seconds` of wall time have been spent (first pass untimed: page faults)."""
@@ -553,6 +583,9 @@ def run_ours(args):
         cpu = {'value': mpix, 'unit': UNIT, 'cores': threads, 'kind': 'port', 'host': host_record(),
                'sample': 'oracle/dirt_oracle.c (OpenMP over images x row bands) fwd+bwd on the first %d images of the workload, '
                          '%d passes in %.1f s' % (n_img, reps, dt)}
+        if not args.no_numpy_baseline:
+            cpu['variants'] = numpy_baselines(scene, prep.grad_pixels_host, threads)
+            cpu['variants']['c_openmp'] = {'value': mpix, 'unit': UNIT, 'cores': threads}
 
     out = {
         'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3),
@@ -633,7 +666,8 @@ def run_reference(args):
                    'note': 'the reference OpenGL/TensorFlow op cannot run in this image; this is the CPU port of its path '
                            '(oracle/dirt_oracle.c, OpenMP over images x row bands, all host threads) on a bounded sample of the same workload'},
         'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': threads, 'kind': 'port', 'host': host_record(),
-                         'sample': '%d images of the workload per step, %d steps' % (B, args.steps)},
+                         'sample': '%d images of the workload per step, %d steps' % (B, args.steps),
+                         'variants': None if args.no_numpy_baseline else numpy_baselines(scene, gp, host_threads)},
         'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
@@ -676,6 +710,7 @@ def main():
     ap.add_argument('--no-graph', action='store_true', help='launch every step call by call instead of replaying a CUDA graph')
     ap.add_argument('--e2e-chunks', type=int, default=8, help='batch chunks of the host copy/compute pipeline')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-numpy-baseline', action='store_true', help='skip the numpy variants of the CPU baseline')
     ap.add_argument('--check', action='store_true', help='after timing, validate the benched buffers against the CPU oracle ("checked": true)')
     ap.add_argument('--no-numa-bind', action='store_true', help='do not pin the process to the NUMA node of its GPU')
     args = ap.parse_args()

@@ -29,7 +29,7 @@ def lib():
     global _lib
     if _lib is not None:
         return _lib
-    path = _build.SO_PATH
+    path = os.environ.get('DIRT_B200_LIB') or _build.SO_PATH   # the override serves A/B timing of prebuilt variants (profiles/kbench.py)
     if not os.path.exists(path):
         raise RuntimeError(
             'dirt_b200: %s is missing; rasterisation is unavailable. Build it with '

@@ -312,16 +312,28 @@ static inline void tri_gbuffer(const Tri* t, int col, int row, float out[4])
     out[3] = cw;
 }
 
-/* visibility of rows [rb, re) of one image: face_ids / keys hold (re - rb) * W entries, row rb first; tris[F] filled on
- * return.  (Work is split over images and, when there are fewer images than threads, over bands of rows: a band only
- * needs the faces clipped to its rows, and the result per pixel does not depend on the split.) */
-static void visibility_rows(const float* verts, const int32_t* faces, int V, int F, int H, int W,
-                            Tri* tris, int32_t* face_ids, uint32_t* keys, int rb, int re)
+/* per-face setup of a whole batch, every (image, face) once, all threads: tris[B*F].  NULL if out of memory. */
+static Tri* setup_batch(const float* vertices, const int32_t* faces, int B, int V, int F, int H, int W)
+{
+    Tri* tris = (Tri*)malloc(sizeof(Tri) * ((size_t)B * F > 0 ? (size_t)B * F : 1));
+    if (!tris) return NULL;
+    const long long total = (long long)B * F;
+#pragma omp parallel for schedule(static)
+    for (long long i = 0; i < total; ++i) {
+        const int b = (int)(i / F);
+        setup_tri(vertices + (size_t)b * V * 4, faces + (size_t)i * 3, V, H, W, &tris[i]);
+    }
+    return tris;
+}
+
+/* visibility of rows [rb, re) of one image from its setup records tris[F]: face_ids / keys hold (re - rb) * W entries,
+ * row rb first.  (Work is split over images and, when there are fewer images than threads, over bands of rows: a band
+ * only needs the faces clipped to its rows, and the result per pixel does not depend on the split.) */
+static void visibility_rows(int F, int W, const Tri* tris, int32_t* face_ids, uint32_t* keys, int rb, int re)
 {
     for (int i = 0; i < (re - rb) * W; ++i) { face_ids[i] = -1; keys[i] = KEY_EMPTY; }
     for (int f = 0; f < F; ++f) {
-        Tri* t = &tris[f];
-        setup_tri(verts, faces + (size_t)f * 3, V, H, W, t);
+        const Tri* t = &tris[f];
         if (t->kind == 0) continue;
         const int r0 = t->rmin > rb ? t->rmin : rb, r1 = t->rmax < re - 1 ? t->rmax : re - 1;
         for (int r = r0; r <= r1; ++r)
@@ -392,15 +404,17 @@ int dirt_oracle_visibility(const float* vertices, const int32_t* faces, int32_t*
     if (B < 0 || H <= 0 || W <= 0 || V < 0 || F < 0) return -1;
     int fail = 0;
     const int NB = bands_per_image(B, H);
+    Tri* all_tris = setup_batch(vertices, faces, B, V, F, H, W);
+    if (!all_tris) return -2;
 #pragma omp parallel for schedule(dynamic, 1)
     for (int item = 0; item < B * NB; ++item) {
         const int b = item / NB, band = item % NB;
         const int rb = (int)((long long)H * band / NB), re = (int)((long long)H * (band + 1) / NB);
-        Tri* tris = (Tri*)malloc(sizeof(Tri) * (size_t)(F > 0 ? F : 1));
+        const Tri* tris = all_tris + (size_t)b * F;
         int32_t* ids = (int32_t*)malloc(sizeof(int32_t) * (size_t)(re - rb) * W);
         uint32_t* keys = (uint32_t*)malloc(sizeof(uint32_t) * (size_t)(re - rb) * W);
-        if (!tris || !ids || !keys) { fail = 1; free(tris); free(ids); free(keys); continue; }
-        visibility_rows(vertices + (size_t)b * V * 4, faces + (size_t)b * F * 3, V, F, H, W, tris, ids, keys, rb, re);
+        if (!ids || !keys) { fail = 1; free(ids); free(keys); continue; }
+        visibility_rows(F, W, tris, ids, keys, rb, re);
         if (face_ids) memcpy(face_ids + ((size_t)b * H + rb) * W, ids, sizeof(int32_t) * (size_t)(re - rb) * W);
         if (gbuffer)
             for (int r = rb; r < re; ++r)
@@ -410,8 +424,9 @@ int dirt_oracle_visibility(const float* vertices, const int32_t* faces, int32_t*
                     if (f < 0) { g[0] = g[1] = g[2] = -1.0f; g[3] = INFINITY; }
                     else tri_gbuffer(&tris[f], c, r, g);
                 }
-        free(tris); free(ids); free(keys);
+        free(ids); free(keys);
     }
+    free(all_tris);
     return fail ? -2 : 0;
 }
 
@@ -422,15 +437,17 @@ int dirt_oracle_forward(const float* background, const float* vertices, const fl
     if (B < 0 || H <= 0 || W <= 0 || C <= 0 || V < 0 || F < 0) return -1;
     int fail = 0;
     const int NB = bands_per_image(B, H);
+    Tri* all_tris = setup_batch(vertices, faces, B, V, F, H, W);
+    if (!all_tris) return -2;
 #pragma omp parallel for schedule(dynamic, 1)
     for (int item = 0; item < B * NB; ++item) {
         const int b = item / NB, band = item % NB;
         const int rb = (int)((long long)H * band / NB), re = (int)((long long)H * (band + 1) / NB);
-        Tri* tris = (Tri*)malloc(sizeof(Tri) * (size_t)(F > 0 ? F : 1));
+        const Tri* tris = all_tris + (size_t)b * F;
         int32_t* ids = (int32_t*)malloc(sizeof(int32_t) * (size_t)(re - rb) * W);
         uint32_t* keys = (uint32_t*)malloc(sizeof(uint32_t) * (size_t)(re - rb) * W);
-        if (!tris || !ids || !keys) { fail = 1; free(tris); free(ids); free(keys); continue; }
-        visibility_rows(vertices + (size_t)b * V * 4, faces + (size_t)b * F * 3, V, F, H, W, tris, ids, keys, rb, re);
+        if (!ids || !keys) { fail = 1; free(ids); free(keys); continue; }
+        visibility_rows(F, W, tris, ids, keys, rb, re);
         const float* cols = vertex_colors + (size_t)b * V * C;
         for (int r = rb; r < re; ++r)
             for (int c = 0; c < W; ++c) {
@@ -453,8 +470,9 @@ int dirt_oracle_forward(const float* background, const float* vertices, const fl
                 }
             }
         if (face_ids_out) memcpy(face_ids_out + ((size_t)b * H + rb) * W, ids, sizeof(int32_t) * (size_t)(re - rb) * W);
-        free(tris); free(ids); free(keys);
+        free(ids); free(keys);
     }
+    free(all_tris);
     return fail ? -2 : 0;
 }
 
@@ -606,23 +624,24 @@ int dirt_oracle_backward(const float* vertices, const int32_t* faces, const floa
     const size_t nv = (size_t)(V > 0 ? V : 1);
     double* gv_all = (double*)calloc((size_t)(B > 0 ? B : 1) * NB * nv * 4, sizeof(double));
     double* gc_all = (double*)calloc((size_t)(B > 0 ? B : 1) * NB * nv * C, sizeof(double));
-    if (!gv_all || !gc_all) { free(gv_all); free(gc_all); free(groups); return -2; }
+    Tri* all_tris = setup_batch(vertices, faces, B, V, F, H, W);
+    if (!gv_all || !gc_all || !all_tris) { free(gv_all); free(gc_all); free(all_tris); free(groups); return -2; }
 #pragma omp parallel for schedule(dynamic, 1)
     for (int item = 0; item < B * NB; ++item) {
         const int b = item / NB, band = item % NB;
         const int r0 = (int)((long long)H * band / NB), r1 = (int)((long long)H * (band + 1) / NB);
         const int rb = r0 > 0 ? r0 - 1 : 0, re = r1 < H ? r1 + 1 : H;   /* the dilation looks one row up and down */
-        Tri* tris = (Tri*)malloc(sizeof(Tri) * (size_t)(F > 0 ? F : 1));
+        const Tri* tris = all_tris + (size_t)b * F;
         int32_t* ids = (int32_t*)malloc(sizeof(int32_t) * (size_t)(re - rb) * W);
         uint32_t* keys = (uint32_t*)malloc(sizeof(uint32_t) * (size_t)(re - rb) * W);
-        if (!tris || !ids || !keys) {
-            fail = 1; free(tris); free(ids); free(keys);
+        if (!ids || !keys) {
+            fail = 1; free(ids); free(keys);
             continue;
         }
         double* gv = gv_all + (size_t)item * nv * 4;
         double* gc = gc_all + (size_t)item * nv * C;
         const float* verts = vertices + (size_t)b * V * 4;
-        visibility_rows(verts, faces + (size_t)b * F * 3, V, F, H, W, tris, ids, keys, rb, re);
+        visibility_rows(F, W, tris, ids, keys, rb, re);
         /* colour gradients and background gradient (:135-148): undilated barycentrics, all channels */
         for (int r = r0; r < r1; ++r)
             for (int c = 0; c < W; ++c) {
@@ -644,8 +663,9 @@ int dirt_oracle_backward(const float* vertices, const int32_t* faces, const floa
             backward_image_group(verts, tris, ids, rb, pixels, grad_pixels, gv, b, B, H, W, C, c0, groups[gi], r0, r1);
             c0 += groups[gi];
         }
-        free(tris); free(ids); free(keys);
+        free(ids); free(keys);
     }
+    free(all_tris);
 #pragma omp parallel for schedule(static)
     for (int b = 0; b < B; ++b) {
         for (size_t i = 0; i < (size_t)V * 4; ++i) {

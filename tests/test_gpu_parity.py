@@ -456,3 +456,23 @@ def test_pixel_jacobians_of_the_cylinder(cuda_lib, oracle):
             np.testing.assert_allclose(translation.grad.cpu().numpy(), t_cpu.grad.numpy(), rtol=1e-4, atol=1e-6 * float(np.abs(gv_o).max() + 1))
             np.testing.assert_array_equal(bg.grad.cpu().numpy(), gb_o[0])
             assert rel_close(col.grad.cpu().numpy(), gc_o[0])[0]
+
+
+def test_bin_overflow_paths(cuda_lib, oracle):
+    # one-pass binning: a tile's bin holds 64 references; the rest goes to the image's overflow list, and when that is
+    # full too (more than 4 entries per face of the image) to the large list.  200 stacked faces of ~4x4 tiles each:
+    # 3200 references against 16 bins x 64 and an overflow list of 800 -> all three levels are exercised.
+    rng = np.random.default_rng(12)
+    n, W, H = 200, 96, 64
+    centre = np.array([0.1, -0.05])
+    tri = rng.uniform(-0.28, 0.28, size=(n, 3, 2)) + centre
+    z = rng.uniform(-0.8, 0.8, size=(n, 3, 1))
+    verts = np.concatenate([tri, z, np.ones((n, 3, 1))], axis=2).reshape(1, n * 3, 4).astype(np.float32)
+    s = dict(background=rng.uniform(size=(1, H, W, 3)).astype(np.float32), vertices=verts,
+             vertex_colors=rng.uniform(size=(1, n * 3, 3)).astype(np.float32),
+             faces=np.arange(n * 3, dtype=np.int32).reshape(1, n, 3))
+    _check_scene(oracle, s, label='bin overflow')
+    # two images with different loads: the lists are per image
+    s2 = {k: np.concatenate([v, v], axis=0) for k, v in s.items()}
+    s2['faces'][1, 50:] = 0   # image 1: 50 real faces, the rest degenerate
+    _check_scene(oracle, s2, label='bin overflow, two images')

@@ -281,3 +281,49 @@ def test_position_gradient_has_the_sign_and_size_of_a_moving_square(oracle):
     want = -256. * H / 2
     assert abs(gv[0, :, 1].sum() - want) < 0.1 * abs(want) and abs(gv[0, :, 0].sum()) < 0.15 * abs(want)
     assert (gv[..., 2] == 0).all()
+
+
+# ---- the vectorised numpy rasteriser (oracle/numpy_raster.py): third implementation, CPU-baseline variant ------------
+
+@pytest.mark.parametrize('name,kwargs', [
+    ('square_scene', dict()),
+    ('cylinder_scene', dict()),
+    ('bent_square_scene', dict(channels=4)),
+    ('bent_square_scene', dict(channels=1)),
+    ('random_soup', dict(batch=2, width=61, height=45, n_faces=70, channels=3, seed=1, behind_camera=True)),
+    ('config3', dict(batch=1, width=96, height=80, level=2, background='uniform')),
+])
+def test_numpy_rasteriser_agrees_with_the_c_oracle(oracle, name, kwargs):
+    from oracle import numpy_raster as npr
+    from conftest import rel_close
+    s = getattr(scenes, name)(**kwargs)
+    B = s['background'].shape[0]
+    pixels_o, ids_o = oracle.forward(**s, return_face_ids=True)
+    gp = np.random.default_rng(0).standard_normal(pixels_o.shape).astype(np.float32)
+    gb_o, gv_o, gc_o = oracle.backward(s['vertices'], s['faces'], pixels_o, gp)
+    for b in range(B):
+        pixels, ids = npr.forward(s['background'][b], s['vertices'][b], s['vertex_colors'][b], s['faces'][b])[:2]
+        np.testing.assert_array_equal(ids, ids_o[b])
+        assert rel_close(pixels, pixels_o[b])[0]
+        head = pixels_o[b + 1].reshape(-1, pixels_o.shape[-1])[:2] if b + 1 < B else None
+        gb, gv, gc = npr.backward(s['vertices'][b], s['faces'][b], pixels_o[b], gp[b], None, head)
+        np.testing.assert_array_equal(gb, gb_o[b])
+        assert rel_close(gv, gv_o[b])[0] and rel_close(gc, gc_o[b])[0]
+
+
+def test_numpy_rasteriser_square_golden():
+    # BASELINE cfg1 through the numpy path: the reference's own acceptance check (tests/square_test.py:54-57)
+    from oracle import numpy_raster as npr
+    s = scenes.square_scene()
+    pixels = npr.forward(s['background'][0], s['vertices'][0], s['vertex_colors'][0], s['faces'][0])[0]
+    np.testing.assert_array_equal(pixels[:, :, 0], np.load(os.path.join(GOLDEN, 'square_test_expected.npy')))
+
+
+def test_numpy_batch_driver_with_processes():
+    from oracle import numpy_raster as npr
+    s = scenes.config3(batch=3, width=64, height=48, level=1)
+    gp = np.random.default_rng(1).standard_normal(s['background'].shape).astype(np.float32)
+    one = npr.forward_backward_batch(s, gp, processes=1)
+    two = npr.forward_backward_batch(s, gp, processes=2)
+    for a, b in zip(one, two):
+        np.testing.assert_array_equal(a, b)
