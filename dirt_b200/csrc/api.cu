@@ -69,10 +69,11 @@ extern "C" int dirt_last_launch_count(void) { return t_last_launches; }
 static bool shape_ok(int B, int H, int W, int C, int V, int F)
 {
     if (B < 0 || H <= 0 || W <= 0 || C <= 0 || V < 0 || F < 0) return false;
-    if (C > 3 * MAX_GROUPS) return false;
+    if (C / 3 + C % 3 > MAX_GROUPS) return false;             // the greedy split of C (groups of 3, then of 1) must fit GroupSpec
     if ((long long)H * W > (1ll << 30)) return false;         // row*W+col stays in int32
     if ((long long)W > (1 << 18) || (long long)H > (1 << 18)) return false;
     if ((long long)B * F > (1ll << 31) - 1) return false;
+    if ((long long)B * ((W + TILE_W - 1) / TILE_W) * ((H + TILE_H - 1) / TILE_H) > (1ll << 31) - 1) return false;   // tile indices are int32
     return true;
 }
 

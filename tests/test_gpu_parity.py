@@ -43,7 +43,7 @@ def _check_scene(oracle, s, seed=0, groups=None, label=''):
     pixels_o, ids_o = oracle.forward(**s, return_face_ids=True)
     pixels_g, ids_g = _forward(s)
     np.testing.assert_array_equal(ids_g, ids_o, err_msg=label + ': face ids differ')
-    ok, ratio = rel_close(pixels_g, pixels_o)
+    ok, ratio = rel_close(pixels_g, pixels_o, name='pixels vs oracle')
     assert ok, '%s: pixels off by %.2fx the tolerance' % (label, ratio)
     gp = np.random.default_rng(seed).standard_normal(pixels_o.shape).astype(np.float32)
     gb_o, gv_o, gc_o = oracle.backward(s['vertices'], s['faces'], pixels_o, gp, groups)
@@ -51,7 +51,7 @@ def _check_scene(oracle, s, seed=0, groups=None, label=''):
         gb_g, gv_g, gc_g = _backward(s, pixels_o, gp, ids_arg, groups)
         np.testing.assert_array_equal(gb_g, gb_o, err_msg=label + ': grad_background differs')
         for name, a, b in (('grad_vertices', gv_g, gv_o), ('grad_vertex_colors', gc_g, gc_o)):
-            ok, ratio = rel_close(a, b)
+            ok, ratio = rel_close(a, b, name=name + ' vs oracle')
             assert ok, '%s: %s off by %.2fx the tolerance' % (label, name, ratio)
         assert (gv_g[..., 2] == 0).all()
     return pixels_g, ids_g

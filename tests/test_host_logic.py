@@ -80,6 +80,14 @@ def test_c_abi_rejects_bad_arguments():
                                      0, null, 0, null) == _lib.ERR_TOO_MANY_VERTICES
     # B == 0 is a no-op, as an empty batch is for the reference
     assert L.dirt_rasterise_forward(null, null, null, null, null, null, 0, 8, 8, 3, 4, 2, null, 0, null) == 0
+    # channel counts whose greedy split into groups of 3 and 1 would not fit the group table are a shape error up front
+    # (384 = 128 groups of 3 fits, 383 = 127 + 2 does not), the same answer from forward and backward
+    assert L.dirt_workspace_bytes(1, 8, 8, 384, 4, 2) > 0 and L.dirt_workspace_bytes(1, 8, 8, 383, 4, 2) == 0
+    assert L.dirt_rasterise_backward(null, null, null, null, null, null, null, null, 1, 8, 8, 383, 4, 2, None, 0, 0, null, 0,
+                                     null) == _lib.ERR_BAD_SHAPE
+    # unknown flag bits of the extended backward entry point
+    assert L.dirt_rasterise_backward_ex(null, null, null, null, null, null, null, null, 1, 8, 8, 3, 4, 2, None, 0, 0, 64,
+                                        null, 0, null) == _lib.ERR_BAD_SHAPE
 
 
 def test_matrices_and_lighting_helpers():

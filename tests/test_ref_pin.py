@@ -42,7 +42,7 @@ def test_oracle_matches_reference_kernel(oracle, path):
     gb, gv, gc = oracle.backward(d['vertices'], d['faces'], d['pixels'], d['grad_pixels'], groups)
     np.testing.assert_array_equal(gb, d['ref_grad_background'])
     for name, got, want in (('grad_vertices', gv, d['ref_grad_vertices']), ('grad_vertex_colors', gc, d['ref_grad_vertex_colors'])):
-        ok, ratio = rel_close(got, want, rel=2e-5)
+        ok, ratio = rel_close(got, want, rel=2e-5, name='oracle %s vs reference kernel' % name)
         assert ok, '%s: oracle %s off by %.2fx the tolerance from the reference kernel' % (_name(path), name, ratio)
     assert (d['ref_grad_vertices'][..., 2] == 0).all()
 
@@ -61,7 +61,7 @@ def test_cuda_matches_reference_kernel(cuda_lib, path):
         gb, gv, gc = ops.rasterise_backward_raw(t['vertices'], t['faces'], t['pixels'], t['grad_pixels'], ids_arg, groups)
         np.testing.assert_array_equal(gb.cpu().numpy(), d['ref_grad_background'])
         for name, got, want in (('grad_vertices', gv, d['ref_grad_vertices']), ('grad_vertex_colors', gc, d['ref_grad_vertex_colors'])):
-            ok, ratio = rel_close(got.cpu().numpy(), want)
+            ok, ratio = rel_close(got.cpu().numpy(), want, name='CUDA %s vs reference kernel' % name)
             assert ok, '%s: CUDA %s off by %.2fx the tolerance from the reference kernel' % (_name(path), name, ratio)
 
 
@@ -101,7 +101,7 @@ def test_live_reference_kernel(cuda_lib, oracle, gen, kwargs, groups):
                                                   torch.from_numpy(gp).cuda(), torch.from_numpy(ids).cuda(), groups)
     np.testing.assert_array_equal(gb_g.cpu().numpy(), gb_r)
     for name, got, want in (('grad_vertices', gv_g, gv_r), ('grad_vertex_colors', gc_g, gc_r)):
-        ok, ratio = rel_close(got.cpu().numpy(), want)
+        ok, ratio = rel_close(got.cpu().numpy(), want, name='CUDA %s vs reference kernel' % name)
         assert ok, '%s: CUDA %s off by %.2fx the tolerance from the reference kernel' % (gen, name, ratio)
 
 
