@@ -345,7 +345,8 @@ template <int C>
 __device__ __noinline__ void tile_generic(const float* __restrict__ vertices, const float* __restrict__ pixels,
                                           const float* __restrict__ grad_pixels, const int32_t* __restrict__ face_ids,
                                           float* __restrict__ gverts, float* __restrict__ gcols,   // rows of this image (or the shared rows); gcols at the group's first channel
-                                          const TriInterp* __restrict__ itp_b, const Frame d, int V, int b, int col, int row0, int cs, int c0)
+                                          const TriInterp* __restrict__ itp_b, const Frame d, int V, int b, int col, int row0, int cs, int c0,
+                                          bool want_pos, bool want_col)
 {
     constexpr int N0 = (C == 1) ? 1 : 3;
     constexpr int NG = (C == 4) ? 2 : 1;
@@ -365,14 +366,14 @@ __device__ __noinline__ void tile_generic(const float* __restrict__ vertices, co
             g_own = exact::gbuffer_at(t_own, col, row);
             const int vid[3] = {t_own.v0, t_own.v1, t_own.v2};
             const float bary[3] = {g_own.x, g_own.y, g_own.z};
-            for (int ch = 0; ch < C; ++ch) {
+            for (int ch = 0; want_col && ch < C; ++ch) {
                 const float gp = __ldg(&grad_pixels[p * cs + c0 + ch]);
 #pragma unroll
                 for (int k = 0; k < 3; ++k) atomicAdd(&gcols[(size_t)vid[k] * cs + ch], gp * bary[k]);
             }
         }
         const bool interior = col > 0 && row > 0 && col < d.W - 1 && row < d.H - 1;
-        for (int gi = 0; gi < NG; ++gi) {
+        for (int gi = 0; want_pos && gi < NG; ++gi) {
             const int g0 = c0 + (gi ? 3 : 0), n = gi ? 1 : N0;
             float sx[3], sy[3];
             if (n == 3) scharr_global<3>(pixels, b, row, col, d, cs, g0, sx, sy);
@@ -642,7 +643,7 @@ __global__ void __launch_bounds__(NW * 32, DIRT_BWD_MIN_BLOCKS * DIRT_BWD_WARPS 
     if (__any_sync(0xffffffffu, overflow)) {
         // more distinct faces than slots: the reference-shaped path for this tile
         if (use_tma && want_pos) { mbar_wait(&bars[1], parity_px); parity_px ^= 1; }
-        tile_generic<C>(vertices, pixels, grad_pixels, face_ids, gverts, gcols, itp_b, Frame{d.B, H, W}, d.V, b, col, row0, cs, c0);
+        tile_generic<C>(vertices, pixels, grad_pixels, face_ids, gverts, gcols, itp_b, Frame{d.B, H, W}, d.V, b, col, row0, cs, c0, want_pos, want_col);
         __syncwarp();
         continue;
     }
