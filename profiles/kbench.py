@@ -8,6 +8,7 @@ Variants are built here with `python profiles/build_variant.py TAG -DFLAG=...` a
 One JSON line per library.
 """
 import argparse
+import ctypes
 import json
 import os
 import subprocess
@@ -58,6 +59,16 @@ def one(args):
            'forward_call_ms': timed(prep.forward, n), 'backward_call_ms': timed(prep.backward, n),
            'step_ms': timed(lambda: prep.local_step(0), n),
            'forward_kernel_ms': kernel(1, prep.forward, n), 'backward_kernel_ms': kernel(2, prep.backward, n)}
+    # the same backward call with per-item vertex gradients ([B,V,.] instead of the batch-accumulated [V,.])
+    B, H, W, C, V, F = prep.dims
+    gv = torch.empty((B, V, 4), device=device); gc = torch.empty((B, V, C), device=device)
+
+    def backward_per_item():
+        stream = ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+        prep.lib.dirt_rasterise_backward(prep._p(prep.vertices), prep._p(prep.faces), prep._p(prep.pixels), prep._p(prep.grad_pixels),
+                                         prep._p(prep.face_ids), prep._p(prep.grad_background), prep._p(gv), prep._p(gc),
+                                         B, H, W, C, V, F, None, 0, 1, prep._p(prep.workspace), prep.ws_bytes, stream)
+    out['backward_kernel_per_item_ms'] = kernel(2, backward_per_item, n)
     prep.capture()
     out['graph_step_ms'] = timed(lambda: prep.graphs[0].replay(), n)
     print(json.dumps(out), flush=True)
