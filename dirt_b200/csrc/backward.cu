@@ -900,6 +900,20 @@ __global__ void __launch_bounds__(NW * 32, DIRT_BWD_MIN_BLOCKS * DIRT_BWD_WARPS 
     }   // b
 }
 
+// sum over the batch of per-item rows: out[i] = sum_b in[b * n + i]  (the two-stage form of BWD_SHARED_GEOMETRY)
+__global__ void __launch_bounds__(256) batch_sum_kernel(const float* __restrict__ in, float* __restrict__ out, int n, int B)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float acc = 0.f;
+    for (int b = 0; b < B; ++b) acc += in[(size_t)b * n + i];
+    out[i] = acc;
+}
+
+#ifndef DIRT_BWD_SHARED_TWO_STAGE
+#define DIRT_BWD_SHARED_TWO_STAGE 0   // 1: accumulate per item into scratch, then one summing pass (instead of atomics on [V,.])
+#endif
+
 // ---- host side --------------------------------------------------------------------------------------------------------
 static PFN_cuTensorMapEncodeTiled tensor_map_encoder()
 {
@@ -956,9 +970,31 @@ cudaError_t launch_backward(const float* vertices, const float* pixels, const fl
                             bool tile_flags_valid, int flags, unsigned long long expect_tag, cudaStream_t stream, int* launches)
 {
     cudaError_t e;
+    // two-stage form of the batch accumulation: per-item rows in scratch (the workspace's own face-id block, free when
+    // the caller supplied the ids), then one summing pass
+    float* out_gv = grad_vertices;
+    float* out_gc = grad_vertex_colors;
+    bool two_stage = false;
+#if DIRT_BWD_SHARED_TWO_STAGE
+    if ((flags & BWD_SHARED_GEOMETRY) && face_ids != ws.face_ids && d.B > 1 &&
+        (size_t)d.B * d.V * (4 + d.C) <= (size_t)d.B * d.H * d.W) {
+        two_stage = true;
+        grad_vertices = reinterpret_cast<float*>(ws.face_ids);
+        grad_vertex_colors = grad_vertices + (size_t)d.B * d.V * 4;
+        flags &= ~BWD_SHARED_GEOMETRY;
+    }
+#endif
     const size_t rows = (size_t)((flags & BWD_SHARED_GEOMETRY) ? 1 : d.B) * d.V;
-    if ((e = cudaMemsetAsync(grad_vertices, 0, sizeof(float) * rows * 4, stream)) != cudaSuccess) return e;
-    if ((e = cudaMemsetAsync(grad_vertex_colors, 0, sizeof(float) * rows * d.C, stream)) != cudaSuccess) return e;
+    if ((e = cudaMemsetAsync(grad_vertices, 0, sizeof(float) * rows * (two_stage ? 4 + d.C : 4), stream)) != cudaSuccess) return e;
+    if (!two_stage && (e = cudaMemsetAsync(grad_vertex_colors, 0, sizeof(float) * rows * d.C, stream)) != cudaSuccess) return e;
+    const auto finish = [&]() -> cudaError_t {
+        if (!two_stage) return cudaSuccess;
+        const int n4 = d.V * 4, nc = d.V * d.C;
+        batch_sum_kernel<<<(n4 + 255) / 256, 256, 0, stream>>>(grad_vertices, out_gv, n4, d.B);
+        batch_sum_kernel<<<(nc + 255) / 256, 256, 0, stream>>>(grad_vertex_colors, out_gc, nc, d.B);
+        *launches += 2;
+        return cudaGetLastError();
+    };
     const long long total_tiles = (long long)d.B * d.btiles;
     if (total_tiles == 0) return cudaSuccess;
     ScopedKernelTimer timer(2, stream);
@@ -986,7 +1022,8 @@ cudaError_t launch_backward(const float* vertices, const float* pixels, const fl
                                                 grad_vertices, grad_vertex_colors, ws, d, tflags, d.C, c0, flags, expect_tag, stream))
     if (fused4) {
         ++*launches;
-        return DIRT_LAUNCH(4, DIRT_BWD_SLOTS_C4, 0);
+        const cudaError_t le = DIRT_LAUNCH(4, DIRT_BWD_SLOTS_C4, 0);
+        return le != cudaSuccess ? le : finish();
     }
     int c0 = 0;
     for (int g = 0; g < groups.n; ++g) {
@@ -996,7 +1033,7 @@ cudaError_t launch_backward(const float* vertices, const float* pixels, const fl
         if (le != cudaSuccess) return le;
     }
 #undef DIRT_LAUNCH
-    return cudaSuccess;
+    return finish();
 }
 
 }  // namespace dirt
