@@ -144,7 +144,7 @@ extern "C" int dirt_rasterise_forward(const float* background, const float* vert
     cudaStream_t stream = (cudaStream_t)cuda_stream;
     const Workspace ws = carve_workspace(workspace, B, H, W, F);
     const Dims d = make_dims(B, H, W, C, V, F);
-    CUDA_TRY(launch_setup_and_bin(vertices, faces, ws, d, stream, &launches));
+    CUDA_TRY(launch_setup_and_bin(vertices, faces, vertex_colors, ws, d, stream, &launches));
     CUDA_TRY(launch_raster_forward(vertices, background, vertex_colors, pixels, face_ids_out, ws, d, stream, &launches));
     t_last_launches = launches;
     return DIRT_OK;
@@ -166,7 +166,7 @@ extern "C" int dirt_rasterise_visibility(const float* vertices, const int32_t* f
     cudaStream_t stream = (cudaStream_t)cuda_stream;
     const Workspace ws = carve_workspace(workspace, B, H, W, F);
     const Dims d = make_dims(B, H, W, 1, V, F);
-    CUDA_TRY(launch_setup_and_bin(vertices, faces, ws, d, stream, &launches));
+    CUDA_TRY(launch_setup_and_bin(vertices, faces, nullptr, ws, d, stream, &launches));
     CUDA_TRY(launch_raster_visibility(vertices, face_ids, gbuffer, ws, d, stream, &launches));
     t_last_launches = launches;
     return DIRT_OK;
@@ -205,7 +205,7 @@ static int backward_impl(const float* vertices, const int32_t* faces, const floa
     unsigned long long expect_tag = 0;
     if (!ids) {
         // no cached visibility: re-derive it exactly as the forward pass does
-        CUDA_TRY(launch_setup_and_bin(vertices, faces, ws, d, stream, &launches));
+        CUDA_TRY(launch_setup_and_bin(vertices, faces, nullptr, ws, d, stream, &launches));
         CUDA_TRY(launch_raster_visibility(vertices, ws.face_ids, nullptr, ws, d, stream, &launches));
         ids = ws.face_ids;
     } else if (!workspace_holds_setup) {

@@ -47,9 +47,6 @@ namespace dirt {
 #ifndef DIRT_BWD_SMALL_FACE
 #define DIRT_BWD_SMALL_FACE 12  // faces owning at most this many records in a tile are added directly (0: always reduce)
 #endif
-#ifndef DIRT_BWD_PREFETCH_GP
-#define DIRT_BWD_PREFETCH_GP 1
-#endif
 #ifndef DIRT_BWD_MIN_BLOCKS
 #define DIRT_BWD_MIN_BLOCKS 8   // x 4 warps: <= 64 registers
 #endif
@@ -243,6 +240,17 @@ __device__ __forceinline__ void scharr_global(const float* __restrict__ pixels, 
     sy[0] = scharr_comp(a_mm.x, a_pm.x, a_mp.x, a_pp.x, a_0m.x, a_0p.x);
     sy[1] = scharr_comp(a_mm.y, a_pm.y, a_mp.y, a_pp.y, a_0m.y, a_0p.y);
     sy[2] = scharr_comp(a_mm.z, a_pm.z, a_mp.z, a_pp.z, a_0m.z, a_0p.z);
+}
+
+// the rare tiles that need it (right frame edge) call it out of line: it is ~1000 instructions when inlined four times
+template <int N0>
+__device__ __noinline__ void scharr_global_call(const float* __restrict__ pixels, int b, int row, int col, int B, int H, int W, int cs,
+                                                int c0, float* sxy)
+{
+    float sx[3], sy[3];
+    scharr_global<N0>(pixels, b, row, col, Frame{B, H, W}, cs, c0, sx, sy);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { sxy[k] = sx[k]; sxy[3 + k] = sy[k]; }
 }
 
 // preferred neighbour offset of the dilation (csrc/rasterise_grad_egl.cu:185-190), as a step in the G-buffer tile:
@@ -519,11 +527,22 @@ __global__ void __launch_bounds__(NW * 32, DIRT_BWD_MIN_BLOCKS * DIRT_BWD_WARPS 
     const size_t p0 = img + (size_t)row0 * W + col;   // pixel 0 of this lane (pixel 1: + W)
     const bool in0 = col < W && row0 < H, in1 = col < W && row0 + 1 < H;
 
-#if DIRT_BWD_PREFETCH_GP
-    // start the DRAM read of this tile's grad_pixels while the tile flag is still on its way
-    if (C == 4 && lane < 8 && trow0 + lane < H && tcol0 < W)
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(grad_pixels + (img + (size_t)(trow0 + lane) * W + tcol0) * 4));
-#endif
+    // ---- grad_pixels of this lane's pixels: needed on every path, so the loads go out before the tile flag is even read
+    float gp[2][C];
+#pragma unroll
+    for (int pix = 0; pix < 2; ++pix) {
+#pragma unroll
+        for (int ch = 0; ch < C; ++ch) gp[pix][ch] = 0.f;
+        if (!(pix ? in1 : in0)) continue;
+        const size_t p = p0 + (size_t)pix * W;
+        if (C == 4) {
+            const float4 v = __ldg(reinterpret_cast<const float4*>(grad_pixels) + p);
+            gp[pix][0] = v.x; gp[pix][1 % C] = v.y; gp[pix][2 % C] = v.z; gp[pix][3 % C] = v.w;
+        } else {
+#pragma unroll
+            for (int ch = 0; ch < C; ++ch) gp[pix][ch] = __ldg(grad_pixels + p * cs + c0 + ch);
+        }
+    }
     const bool flagged = tile_flags == nullptr || tile_flags[(size_t)b * d.tiles + ty * d.tiles_x + (tx >> 1)] != 0;
 
     // ---- (1) stage the halo of face ids and pixels ------------------------------------------------------------------
@@ -558,22 +577,6 @@ __global__ void __launch_bounds__(NW * 32, DIRT_BWD_MIN_BLOCKS * DIRT_BWD_WARPS 
         if (lane < NSLOT) keys[lane] = -1;
     }
 
-    // ---- grad_pixels of this lane's pixels; background-only tiles -----------------------------------------------------
-    float gp[2][C];
-#pragma unroll
-    for (int pix = 0; pix < 2; ++pix) {
-#pragma unroll
-        for (int ch = 0; ch < C; ++ch) gp[pix][ch] = 0.f;
-        if (!(pix ? in1 : in0)) continue;
-        const size_t p = p0 + (size_t)pix * W;
-        if (C == 4) {
-            const float4 v = __ldg(reinterpret_cast<const float4*>(grad_pixels) + p);
-            gp[pix][0] = v.x; gp[pix][1 % C] = v.y; gp[pix][2 % C] = v.z; gp[pix][3 % C] = v.w;
-        } else {
-#pragma unroll
-            for (int ch = 0; ch < C; ++ch) gp[pix][ch] = __ldg(grad_pixels + p * cs + c0 + ch);
-        }
-    }
     auto store_gb = [&](int pix, bool uncovered) {
         // grad_background: grad_pixels where uncovered, 0 elsewhere (:143-148, memset :247)
         const size_t p = p0 + (size_t)pix * W;
@@ -627,6 +630,7 @@ __global__ void __launch_bounds__(NW * 32, DIRT_BWD_MIN_BLOCKS * DIRT_BWD_WARPS 
         int slot = -1;
         if (id >= 0 && lane == leader) {
             int h = (NSLOT == 32) ? (int)(((unsigned)id * 2654435761u) >> 27) : (int)__umulhi((unsigned)id * 2654435761u, (unsigned)NSLOT);
+#pragma unroll 1
             for (int probe = 0; probe < NSLOT; ++probe) {
                 const int old = atomicCAS(&keys[h], -1, id);
                 if (old == -1 || old == id) { slot = h; break; }
@@ -716,8 +720,15 @@ __global__ void __launch_bounds__(NW * 32, DIRT_BWD_MIN_BLOCKS * DIRT_BWD_WARPS 
             if (C == 4) scharr_smem_c4(tile, lrow0 + pix + 1, lcol + 1, sx, sy, sx1, sy1);
             else scharr_smem<C, N0>(tile, lrow0 + pix + 1, lcol + 1, sx, sy);
         } else {
-            scharr_global<N0>(pixels, b, row, col, Frame{d.B, H, W}, cs, c0, sx, sy);
-            if (TWO_GROUPS) scharr_global<1>(pixels, b, row, col, Frame{d.B, H, W}, cs, c0 + 3, sx1, sy1);
+            float t[6];
+            scharr_global_call<N0>(pixels, b, row, col, d.B, H, W, cs, c0, t);
+#pragma unroll
+            for (int k = 0; k < 3; ++k) { sx[k] = t[k]; sy[k] = t[3 + k]; }
+            if (TWO_GROUPS) {
+                scharr_global_call<1>(pixels, b, row, col, d.B, H, W, cs, c0 + 3, t);
+#pragma unroll
+                for (int k = 0; k < 3; ++k) { sx1[k] = t[k]; sy1[k] = t[3 + k]; }
+            }
         }
         float dLdx = 0.f, dLdy = 0.f, gx1 = 0.f, gy1 = 0.f;
 #pragma unroll

@@ -51,6 +51,18 @@ struct __align__(16) TriInterp { // interpolation planes relative to (cref,rref)
 };
 static_assert(sizeof(TriInterp) == 64, "TriInterp must be 64 bytes");
 
+// Forward shading of a face whose tensors have C <= 4 channels: value_c(p) = N_c(p) / S(p), where N_c is the plane of
+// sum_k (beta_k / w_k) * colour_kc and S the plane of 1 / clip_w, both relative to the face's reference pixel.  One
+// 64-byte gather per (pixel, face) instead of the interpolation record plus three vertex-colour rows.
+struct __align__(16) TriShade {
+    float sA, sB, sC;
+    uint32_t ref;        // cref | rref << 16 (frames up to 65536 x 65536)
+    float n[4][3];       // (A, B, C) of N_c, c = 0..3
+};
+static_assert(sizeof(TriShade) == 64, "TriShade must be 64 bytes");
+constexpr int SHADE_MAX_CHANNELS = 4;
+constexpr int SHADE_MAX_EXTENT = 65536;
+
 struct __align__(16) TriXY {     // clip-space x,y of the face's three vertices (the backward pass's clip_x / clip_y,
     float x0, y0, x1, y1;        // csrc/rasterise_grad_egl.cu:210-215): stored next to the planes so that a tile's face
     float x2, y2, pad0, pad1;    // table is filled in one hop
@@ -80,6 +92,7 @@ struct Workspace {
     TriCov* cov;          // [B*F]
     TriInterp* itp;       // [B*F]
     TriXY* xy;            // [B*F]
+    TriShade* shade;      // [B*F]  (written by forward calls with C <= SHADE_MAX_CHANNELS)
     // One-pass binning: the setup kernel appends a face to the bin of every tile its bounding box touches
     // (position = atomicAdd on the tile's count).  A bin holds BIN_CAP references at a fixed place, so the raster
     // kernel fetches a tile's count and its references in ONE hop; what does not fit goes to the image's overflow list
@@ -111,6 +124,7 @@ inline Workspace carve_workspace(void* base, int B, int H, int W, int F)
     ws.cov = (TriCov*)take(BF * sizeof(TriCov));
     ws.itp = (TriInterp*)take(BF * sizeof(TriInterp));
     ws.xy = (TriXY*)take(BF * sizeof(TriXY));
+    ws.shade = (TriShade*)take(BF * sizeof(TriShade));
     // the blocks the forward pass must zero are adjacent: one memset covers [tile_count, zero_end)
     ws.tile_count = (int*)take(BT * sizeof(int));
     ws.tile_flags = (unsigned char*)take(BT);
@@ -312,8 +326,10 @@ struct ScopedKernelTimer {
 // ---- host-side launchers (one per .cu) ----------------------------------------------------------
 // All return cudaError_t of the launch and add the number of kernels they launched to *launches.
 // Both setup launchers leave workspace_tag(vertices, faces, sizes) in the workspace header.
-cudaError_t launch_setup_and_bin(const float* vertices, const int32_t* faces, const Workspace& ws, const Dims& d,
-                                 cudaStream_t stream, int* launches);
+// vertex_colors != nullptr (and shade_records_ok(d)): the shading records are written as well.
+inline bool shade_records_ok(const Dims& d) { return d.C <= SHADE_MAX_CHANNELS && d.W <= SHADE_MAX_EXTENT && d.H <= SHADE_MAX_EXTENT; }
+cudaError_t launch_setup_and_bin(const float* vertices, const int32_t* faces, const float* vertex_colors, const Workspace& ws,
+                                 const Dims& d, cudaStream_t stream, int* launches);
 cudaError_t launch_setup_only(const float* vertices, const int32_t* faces, const Workspace& ws, const Dims& d,
                               cudaStream_t stream, int* launches);
 cudaError_t launch_raster_forward(const float* vertices, const float* background, const float* vertex_colors, float* pixels,

@@ -256,8 +256,35 @@ __device__ __forceinline__ void shade_pixel(const TriInterp& ti, int col, int ro
     }
 }
 
+// The same from the face's shading record (C <= 4): value_c = N_c(p) / S(p), the quotient refined once so that equal vertex
+// colours give exactly that colour (tests/square_test.py) -- no barycentrics, no vertex-colour gathers.
+template <int CT>
+__device__ __forceinline__ void shade_pixel_record(const TriShade* __restrict__ rec, int col, int row, float* __restrict__ out, int C)
+{
+    const float4* r = reinterpret_cast<const float4*>(rec);
+    const float4 v0 = __ldg(r), v1 = __ldg(r + 1), v2 = __ldg(r + 2), v3 = __ldg(r + 3);
+    const uint32_t ref = __float_as_uint(v0.w);
+    const float dc = (float)(col - (int)(ref & 0xffffu)), dr = (float)(row - (int)(ref >> 16));
+    const float S = fmaf(v0.x, dc, fmaf(v0.y, dr, v0.z));
+    const float rs = __fdividef(1.0f, S);
+    auto quotient = [&](float A, float B, float Cc) -> float {
+        const float n = fmaf(A, dc, fmaf(B, dr, Cc));
+        const float q = n * rs;
+        return fmaf(fmaf(-q, S, n), rs, q);
+    };
+    const float o0 = quotient(v1.x, v1.y, v1.z), o1 = quotient(v1.w, v2.x, v2.y), o2 = quotient(v2.z, v2.w, v3.x), o3 = quotient(v3.y, v3.z, v3.w);
+    if (CT == 4) {
+        *reinterpret_cast<float4*>(out) = make_float4(o0, o1, o2, o3);
+    } else {
+        out[0] = o0;
+        if (C > 1) out[1] = o1;
+        if (C > 2) out[2] = o2;
+        if (C > 3) out[3] = o3;
+    }
+}
+
 // MODE 0: colour forward (pixels [+ face ids]); MODE 1: visibility (face ids and/or G-buffer)
-template <int MODE, int CT>
+template <int MODE, int CT, bool REC>
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, DIRT_RASTER_MIN_BLOCKS) raster_kernel(
     const float* __restrict__ vertices, const float* __restrict__ background,
     const float* __restrict__ vertex_colors, float* __restrict__ pixels, int32_t* __restrict__ face_ids_out,
@@ -422,6 +449,8 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, DIRT_RASTER_MIN_BLOCKS) 
             } else {
                 for (int ch = 0; ch < C; ++ch) pixels[p * C + ch] = __ldg(&background[p * C + ch]);
             }
+        } else if (REC) {
+            shade_pixel_record<CT>(ws.shade + (size_t)b * d.F + face, col, row, pixels + p * C, C);
         } else {
             if (face != prev_face) { ti = load_interp(itp_b + face); prev_face = face; }
             shade_pixel<CT>(ti, col, row, cols, pixels + p * C, C);
@@ -442,15 +471,19 @@ cudaError_t launch_raster_forward(const float* vertices, const float* background
                       ((uintptr_t)vertex_colors % 16 == 0);
     // C == 3 with an even width: every quad row (two pixels) is 24 contiguous, 8-byte aligned bytes
     const bool vec3 = d.C == 3 && d.W % 2 == 0 && ((uintptr_t)background % 8 == 0) && ((uintptr_t)pixels % 8 == 0);
-    if (vec4)
-        raster_kernel<0, 4><<<grid, WARPS_PER_BLOCK * 32, 0, stream>>>(vertices, background, vertex_colors, pixels,
-                                                                       face_ids_out, nullptr, ws, d);
-    else if (vec3)
-        raster_kernel<0, 3><<<grid, WARPS_PER_BLOCK * 32, 0, stream>>>(vertices, background, vertex_colors, pixels,
-                                                                       face_ids_out, nullptr, ws, d);
-    else
-        raster_kernel<0, 0><<<grid, WARPS_PER_BLOCK * 32, 0, stream>>>(vertices, background, vertex_colors, pixels,
-                                                                       face_ids_out, nullptr, ws, d);
+    const bool rec = shade_records_ok(d);   // the setup pass of this call wrote the shading records (C <= 4)
+    if (vec4 && rec)
+        raster_kernel<0, 4, true><<<grid, WARPS_PER_BLOCK * 32, 0, stream>>>(vertices, background, vertex_colors, pixels,
+                                                                             face_ids_out, nullptr, ws, d);
+    else if (vec3 && rec)
+        raster_kernel<0, 3, true><<<grid, WARPS_PER_BLOCK * 32, 0, stream>>>(vertices, background, vertex_colors, pixels,
+                                                                             face_ids_out, nullptr, ws, d);
+    else if (rec)
+        raster_kernel<0, 0, true><<<grid, WARPS_PER_BLOCK * 32, 0, stream>>>(vertices, background, vertex_colors, pixels,
+                                                                             face_ids_out, nullptr, ws, d);
+    else   // more than four channels (or a frame beyond the records' 16-bit reference pixel): barycentrics + colour gathers
+        raster_kernel<0, 0, false><<<grid, WARPS_PER_BLOCK * 32, 0, stream>>>(vertices, background, vertex_colors, pixels,
+                                                                              face_ids_out, nullptr, ws, d);
     ++*launches;
     return cudaGetLastError();
 }
@@ -460,7 +493,7 @@ cudaError_t launch_raster_visibility(const float* vertices, int32_t* face_ids, f
 {
     if ((long long)d.B * d.tiles == 0) return cudaSuccess;
     const dim3 grid((unsigned)((d.tiles_x + WARPS_PER_BLOCK * TILES_PER_WARP - 1) / (WARPS_PER_BLOCK * TILES_PER_WARP)), (unsigned)d.tiles_y, (unsigned)min(d.B, 65535));
-    raster_kernel<1, 0><<<grid, WARPS_PER_BLOCK * 32, 0, stream>>>(vertices, nullptr, nullptr, nullptr, face_ids, gbuffer, ws, d);
+    raster_kernel<1, 0, false><<<grid, WARPS_PER_BLOCK * 32, 0, stream>>>(vertices, nullptr, nullptr, nullptr, face_ids, gbuffer, ws, d);
     ++*launches;
     return cudaGetLastError();
 }

@@ -25,7 +25,8 @@ constexpr float GUARD_BAND = 8388608.0f;  // 2^23 sub-pixel units = 32768 px
 #endif
 template <bool BIN>
 __global__ void __launch_bounds__(DIRT_SETUP_THREADS, DIRT_SETUP_MIN_BLOCKS) setup_kernel(const float* __restrict__ vertices,
-                                                    const int32_t* __restrict__ faces, Workspace ws, Dims d)
+                                                    const int32_t* __restrict__ faces, const float* __restrict__ vertex_colors,
+                                                    Workspace ws, Dims d)
 {
     const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long total = (long long)d.B * d.F;
@@ -141,6 +142,32 @@ __global__ void __launch_bounds__(DIRT_SETUP_THREADS, DIRT_SETUP_MIN_BLOCKS) set
         float4* dstx = reinterpret_cast<float4*>(ws.xy + gid);
         dstx[0] = make_float4(p[0][0], p[0][1], p[1][0], p[1][1]);
         dstx[1] = make_float4(p[2][0], p[2][1], 0.f, 0.f);
+        // shading record: planes of N_c = q0*(c0 - c2) + q1*(c1 - c2) + S*c2 (q2 = S - q0 - q1), values only
+        if (BIN && vertex_colors != nullptr) {
+            const float* cols = vertex_colors + (size_t)b * d.V * d.C;
+            float4 out[4];
+            out[0] = make_float4(itp.sA, itp.sB, itp.sC, __uint_as_float((uint32_t)cref | ((uint32_t)rref << 16)));
+            float n[12];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                double c0 = 0.0, c1 = 0.0, c2 = 0.0;
+                if (c < d.C) {
+                    c0 = (double)__ldg(cols + (size_t)vid[0] * d.C + c);
+                    c1 = (double)__ldg(cols + (size_t)vid[1] * d.C + c);
+                    c2 = (double)__ldg(cols + (size_t)vid[2] * d.C + c);
+                }
+                const double d0 = c0 - c2, d1 = c1 - c2;
+                const double nA = gq[0][0] * d0 + gq[1][0] * d1 + gs[0] * c2;
+                const double nB = gq[0][1] * d0 + gq[1][1] * d1 + gs[1] * c2;
+                const double nC = gq[0][2] * d0 + gq[1][2] * d1 + gs[2] * c2;
+                n[3 * c] = (float)nA; n[3 * c + 1] = (float)nB; n[3 * c + 2] = (float)((nA * cr + nB * rr) + nC);
+            }
+            out[1] = make_float4(n[0], n[1], n[2], n[3]);
+            out[2] = make_float4(n[4], n[5], n[6], n[7]);
+            out[3] = make_float4(n[8], n[9], n[10], n[11]);
+            float4* dsts = reinterpret_cast<float4*>(ws.shade + gid);
+            dsts[0] = out[0]; dsts[1] = out[1]; dsts[2] = out[2]; dsts[3] = out[3];
+        }
     }
 
     // tile bounding box and the layout of the coverage record.
@@ -206,14 +233,15 @@ __global__ void __launch_bounds__(DIRT_SETUP_THREADS, DIRT_SETUP_MIN_BLOCKS) set
     }
 }
 
-cudaError_t launch_setup_and_bin(const float* vertices, const int32_t* faces, const Workspace& ws, const Dims& d,
-                                 cudaStream_t stream, int* launches)
+cudaError_t launch_setup_and_bin(const float* vertices, const int32_t* faces, const float* vertex_colors, const Workspace& ws,
+                                 const Dims& d, cudaStream_t stream, int* launches)
 {
+    if (!shade_records_ok(d)) vertex_colors = nullptr;
     const long long total = (long long)d.B * d.F;
     cudaError_t e;
     if ((e = cudaMemsetAsync(ws.tile_count, 0, ws.zero_bytes, stream)) != cudaSuccess) return e;
     if (total > 0) {
-        setup_kernel<true><<<(unsigned)((total + DIRT_SETUP_THREADS - 1) / DIRT_SETUP_THREADS), DIRT_SETUP_THREADS, 0, stream>>>(vertices, faces, ws, d);
+        setup_kernel<true><<<(unsigned)((total + DIRT_SETUP_THREADS - 1) / DIRT_SETUP_THREADS), DIRT_SETUP_THREADS, 0, stream>>>(vertices, faces, vertex_colors, ws, d);
         ++*launches;
     }
     return cudaGetLastError();
@@ -226,7 +254,7 @@ cudaError_t launch_setup_only(const float* vertices, const int32_t* faces, const
     cudaError_t e;
     if ((e = cudaMemsetAsync(ws.header, 0, sizeof(Header), stream)) != cudaSuccess) return e;
     if (total > 0) {
-        setup_kernel<false><<<(unsigned)((total + DIRT_SETUP_THREADS - 1) / DIRT_SETUP_THREADS), DIRT_SETUP_THREADS, 0, stream>>>(vertices, faces, ws, d);
+        setup_kernel<false><<<(unsigned)((total + DIRT_SETUP_THREADS - 1) / DIRT_SETUP_THREADS), DIRT_SETUP_THREADS, 0, stream>>>(vertices, faces, nullptr, ws, d);
         ++*launches;
     }
     return cudaGetLastError();
