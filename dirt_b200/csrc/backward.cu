@@ -64,6 +64,15 @@ constexpr int HALO_ROWS = TILE + 2;   // 10
 constexpr int HALO_COLS = TILE + 4;   // 12: col-1 .. col+10 (one pixel around for the Scharr taps, two more to the right
                                       // for the flat-order reads of 1-wide groups; also makes every TMA box row a multiple of 16 B)
 constexpr int GB_COLS = TILE + 2;     // 10: the G-buffer tile has no use for the two extra columns
+// A TMA box must start on a 16-byte boundary of the innermost dimension (measured: anything else is an illegal-instruction
+// fault, profiles/r02_tma_probe2.txt).  The halo starts one pixel left of a tile whose first column is a multiple of 8, so
+// the staged tiles of 4-byte pixels (face ids, 1- and 3-channel groups) are 16 pixels wide, starting FOUR pixels left of
+// the tile (halo column hc sits at tile column hc + 3); 16-byte pixels (C = 4) keep the 12-pixel row starting at the halo.
+constexpr int IDS_COLS = 16, IDS_COL0 = 3;
+template <int C> struct PxTile {
+    static constexpr int COLS = (C == 4) ? HALO_COLS : 16;   // pixels per staged row
+    static constexpr int COL0 = (C == 4) ? 0 : 3;            // tile column of halo column 0
+};
 
 struct V3 { float x, y, z; };
 
@@ -141,7 +150,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
 // generic-proxy accesses to shared memory (ours) before async-proxy ones (the next TMA write into the same buffer)
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-// TMA: one 3-D box [1][HALO_ROWS][HALO_COLS * elems] of a [B][H][W * elems] tensor into shared memory
+// TMA: one 3-D box [1][HALO_ROWS][box] of a [B][H][W * elems] tensor into shared memory; x (in elements) must be a multiple of 4
 __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* map, int x, int y, int z, uint64_t* bar)
 {
     asm volatile(
@@ -164,8 +173,8 @@ static_assert(sizeof(SlotRec) == 96, "SlotRec must be 96 bytes");
 
 template <int C, int NSLOT>
 struct BwdSmem {
-    static constexpr int PX_BYTES = HALO_ROWS * HALO_COLS * C * 4;
-    static constexpr int IDS_BYTES = HALO_ROWS * HALO_COLS * 4;
+    static constexpr int PX_BYTES = HALO_ROWS * PxTile<C>::COLS * C * 4;
+    static constexpr int IDS_BYTES = HALO_ROWS * IDS_COLS * 4;
     static constexpr int GBUF_BYTES = HALO_ROWS * GB_COLS * 16;
     static constexpr int PX_OFF = 0;
     // the face-id tile is dead once every lane holds its ids and slots: the G-buffer tile reuses its bytes
@@ -178,13 +187,14 @@ struct BwdSmem {
 };
 
 // ---- Scharr sums from the staged tile -------------------------------------------------------------------------------
-// Scharr sums of a single group (width N0) from the staged tile.  lr/lc: pixel position inside the halo tile.
+// Scharr sums of a single group (width N0) from the staged tile.  lr/lc: row / column of the pixel inside the staged tile.
 template <int C, int N0>
 __device__ __forceinline__ void scharr_smem(const float* __restrict__ tile, int lr, int lc, float (&sx)[3], float (&sy)[3])
 {
     // comp k of the tap at (lr+dr, lc+dc): channel k (N0 == 3) or channel 0 of the pixel k places to the right (N0 == 1)
+    constexpr int PITCH = PxTile<C>::COLS;
     auto T = [&](int dr, int dc, int k) -> float {
-        return (N0 == 3) ? tile[((lr + dr) * HALO_COLS + lc + dc) * C + k] : tile[((lr + dr) * HALO_COLS + lc + dc + k) * C];
+        return (N0 == 3) ? tile[((lr + dr) * PITCH + lc + dc) * C + k] : tile[((lr + dr) * PITCH + lc + dc + k) * C];
     };
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
@@ -499,7 +509,8 @@ __global__ void __launch_bounds__(NW * 32, DIRT_BWD_MIN_BLOCKS * DIRT_BWD_WARPS 
     const int g0 = (lrow0 + 1) * GB_COLS + lcol + 1;                  // G-buffer tile index of pixel 0 (pixel 1: + GB_COLS)
     const int ring_r = lane < 8 ? 0 : lane < 16 ? TILE + 1 : lane - (lane < 24 ? 15 : 23);
     const int ring_c = lane < 8 ? lane + 1 : lane < 16 ? lane - 7 : lane < 24 ? 0 : TILE + 1;
-    // whole halo inside the frame (and the 12-wide TMA box too): no clamping, every pixel is interior
+    // whole halo (12 columns: the flat-order reads reach two past the 10) inside the frame: no clamping, every pixel is
+    // interior.  (What a 16-wide TMA box holds beyond the halo may be out of bounds: zero-filled, never read.)
     const bool inner = tcol0 >= 1 && trow0 >= 1 && tcol0 + HALO_COLS - 2 <= W - 1 && trow0 + TILE <= H - 1;
     const bool use_tma = USE_TMA && inner;   // warp-uniform
     const bool per_item = !(flags & BWD_SHARED_GEOMETRY);
@@ -551,25 +562,27 @@ __global__ void __launch_bounds__(NW * 32, DIRT_BWD_MIN_BLOCKS * DIRT_BWD_WARPS 
             if (lane == 0) {
                 fence_proxy_async();
                 mbar_expect_tx(&bars[0], SM::IDS_BYTES);
-                tma_load_3d(ids_tile, &ids_map, tcol0 - 1, trow0 - 1, b, &bars[0]);
+                tma_load_3d(ids_tile, &ids_map, tcol0 - 1 - IDS_COL0, trow0 - 1, b, &bars[0]);
                 if (want_pos) {
                     mbar_expect_tx(&bars[1], SM::PX_BYTES);
-                    tma_load_3d(tile, &px_map, (tcol0 - 1) * C, trow0 - 1, b, &bars[1]);
+                    tma_load_3d(tile, &px_map, (tcol0 - 1 - PxTile<C>::COL0) * C, trow0 - 1, b, &bars[1]);
                 }
             }
         } else {
             for (int e = lane; e < HALO_ROWS * HALO_COLS; e += 32) {
                 const int hr = e / HALO_COLS, hc = e - hr * HALO_COLS;
                 const int r = trow0 - 1 + hr, c = tcol0 - 1 + hc;
-                if (r >= 0 && r < H && c >= 0 && c < W) cp_async_4(ids_tile + e, face_ids + img + (size_t)r * W + c);
-                else ids_tile[e] = -1;
+                int* const id_dst = ids_tile + hr * IDS_COLS + hc + IDS_COL0;
+                if (r >= 0 && r < H && c >= 0 && c < W) cp_async_4(id_dst, face_ids + img + (size_t)r * W + c);
+                else *id_dst = -1;
                 if (!want_pos) continue;
                 const int rc = max(0, min(H - 1, r)), cc = max(0, min(W - 1, c));
                 const float* src = pixels + (img + (size_t)rc * W + cc) * cs + c0;
-                if (C == 4) cp_async_16(tile + e * 4, src);
+                float* const px_dst = tile + (hr * PxTile<C>::COLS + hc + PxTile<C>::COL0) * C;
+                if (C == 4) cp_async_16(px_dst, src);
                 else {
 #pragma unroll
-                    for (int ch = 0; ch < C; ++ch) cp_async_4(tile + e * C + ch, src + ch);
+                    for (int ch = 0; ch < C; ++ch) cp_async_4(px_dst + ch, src + ch);
                 }
             }
             cp_async_commit();
@@ -599,8 +612,8 @@ __global__ void __launch_bounds__(NW * 32, DIRT_BWD_MIN_BLOCKS * DIRT_BWD_WARPS 
     if (use_tma) { mbar_wait(&bars[0], parity_ids); parity_ids ^= 1; }
     else cp_async_wait_all();
     __syncwarp();
-    const int i0 = (lrow0 + 1) * HALO_COLS + lcol + 1;
-    const int id0 = ids_tile[i0], id1 = ids_tile[i0 + HALO_COLS], idr = ids_tile[ring_r * HALO_COLS + ring_c];
+    const int i0 = (lrow0 + 1) * IDS_COLS + lcol + 1 + IDS_COL0;
+    const int id0 = ids_tile[i0], id1 = ids_tile[i0 + IDS_COLS], idr = ids_tile[ring_r * IDS_COLS + ring_c + IDS_COL0];
     if (want_col && in0) store_gb(0, id0 < 0);
     if (want_col && in1) store_gb(1, id1 < 0);
     if (!__any_sync(0xffffffffu, (id0 & id1 & idr) >= 0)) {
@@ -611,8 +624,8 @@ __global__ void __launch_bounds__(NW * 32, DIRT_BWD_MIN_BLOCKS * DIRT_BWD_WARPS 
     // per pixel: covered, or (interior pixels only) a covered 4-neighbour that could dilate into it
     bool near0, near1, interior0 = true, interior1 = true;
     {
-        const int up0 = ids_tile[i0 - HALO_COLS], l0 = ids_tile[i0 - 1], r0 = ids_tile[i0 + 1];
-        const int l1 = ids_tile[i0 + HALO_COLS - 1], r1 = ids_tile[i0 + HALO_COLS + 1], dn1 = ids_tile[i0 + 2 * HALO_COLS];
+        const int up0 = ids_tile[i0 - IDS_COLS], l0 = ids_tile[i0 - 1], r0 = ids_tile[i0 + 1];
+        const int l1 = ids_tile[i0 + IDS_COLS - 1], r1 = ids_tile[i0 + IDS_COLS + 1], dn1 = ids_tile[i0 + 2 * IDS_COLS];
         if (!inner) {
             interior0 = col > 0 && row0 > 0 && col < W - 1 && row0 < H - 1;
             interior1 = col > 0 && row0 + 1 < H - 1 && col < W - 1;
@@ -718,7 +731,7 @@ __global__ void __launch_bounds__(NW * 32, DIRT_BWD_MIN_BLOCKS * DIRT_BWD_WARPS 
         float sx[3], sy[3], sx1[3], sy1[3];
         if (staged_taps) {
             if (C == 4) scharr_smem_c4(tile, lrow0 + pix + 1, lcol + 1, sx, sy, sx1, sy1);
-            else scharr_smem<C, N0>(tile, lrow0 + pix + 1, lcol + 1, sx, sy);
+            else scharr_smem<C, N0>(tile, lrow0 + pix + 1, lcol + 1 + PxTile<C>::COL0, sx, sy);
         } else {
             float t[6];
             scharr_global_call<N0>(pixels, b, row, col, d.B, H, W, cs, c0, t);
@@ -938,14 +951,14 @@ static PFN_cuTensorMapEncodeTiled tensor_map_encoder()
     return fn;
 }
 
-// [B][H][W*elems] tensor of 4-byte elements, box [1][HALO_ROWS][HALO_COLS*elems]
-static bool make_tile_map(CUtensorMap* map, const void* base, CUtensorMapDataType type, int B, int H, int W, int elems)
+// [B][H][W*elems] tensor of 4-byte elements, box [1][HALO_ROWS][box_pixels*elems]
+static bool make_tile_map(CUtensorMap* map, const void* base, CUtensorMapDataType type, int B, int H, int W, int elems, int box_pixels)
 {
     PFN_cuTensorMapEncodeTiled enc = tensor_map_encoder();
     if (!enc) return false;
     const cuuint64_t dims[3] = {(cuuint64_t)W * elems, (cuuint64_t)H, (cuuint64_t)B};
     const cuuint64_t strides[2] = {(cuuint64_t)W * elems * 4, (cuuint64_t)H * W * elems * 4};
-    const cuuint32_t box[3] = {(cuuint32_t)(HALO_COLS * elems), (cuuint32_t)HALO_ROWS, 1u};
+    const cuuint32_t box[3] = {(cuuint32_t)(box_pixels * elems), (cuuint32_t)HALO_ROWS, 1u};
     const cuuint32_t estr[3] = {1u, 1u, 1u};
     return enc(map, type, 3, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
@@ -1024,8 +1037,8 @@ cudaError_t launch_backward(const float* vertices, const float* pixels, const fl
     bool tma = DIRT_BWD_TMA && pixels && (d.C == 1 || d.C == 3 || fused4) && groups.n == (fused4 ? 2 : 1) && d.W % 4 == 0 &&
                ((uintptr_t)pixels % 16 == 0) && ((uintptr_t)face_ids % 16 == 0);
     if (tma)
-        tma = make_tile_map(&px_map, pixels, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, d.B, d.H, d.W, d.C) &&
-              make_tile_map(&ids_map, face_ids, CU_TENSOR_MAP_DATA_TYPE_INT32, d.B, d.H, d.W, 1);
+        tma = make_tile_map(&px_map, pixels, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, d.B, d.H, d.W, d.C, d.C == 4 ? PxTile<4>::COLS : PxTile<3>::COLS) &&
+              make_tile_map(&ids_map, face_ids, CU_TENSOR_MAP_DATA_TYPE_INT32, d.B, d.H, d.W, 1, IDS_COLS);
 #define DIRT_LAUNCH(CC, NSLOT, c0)                                                                                             \
     (tma ? launch_tile_kernel<CC, NSLOT, true>(px_map, ids_map, vertices, pixels, grad_pixels, face_ids, grad_background,       \
                                                grad_vertices, grad_vertex_colors, ws, d, tflags, d.C, c0, flags, expect_tag, stream)               \
