@@ -27,9 +27,6 @@ import time
 
 import numpy as np
 
-# stable placement of the OpenMP threads of the CPU legs (read by libgomp when oracle/libdirt_oracle.so is loaded)
-os.environ.setdefault('OMP_PROC_BIND', 'true')
-os.environ.setdefault('OMP_PLACES', 'threads')
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:

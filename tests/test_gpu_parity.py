@@ -459,11 +459,11 @@ def test_pixel_jacobians_of_the_cylinder(cuda_lib, oracle):
 
 
 def test_bin_overflow_paths(cuda_lib, oracle):
-    # one-pass binning: a tile's bin holds 64 references; the rest goes to the image's overflow list, and when that is
-    # full too (more than 4 entries per face of the image) to the large list.  200 stacked faces of ~4x4 tiles each:
-    # 3200 references against 16 bins x 64 and an overflow list of 800 -> all three levels are exercised.
+    # one-pass binning: a tile's bin holds 128 references; the rest goes to the overflow list of the tile's row of tiles
+    # (1024 entries per row and image), and when that is full too to the image's large list.  600 stacked faces of ~4x4
+    # tiles each: ~600 references per tile against bins of 128 and ~1900 overflow entries per row -> all three levels.
     rng = np.random.default_rng(12)
-    n, W, H = 200, 96, 64
+    n, W, H = 600, 96, 64
     centre = np.array([0.1, -0.05])
     tri = rng.uniform(-0.28, 0.28, size=(n, 3, 2)) + centre
     z = rng.uniform(-0.8, 0.8, size=(n, 3, 1))
@@ -474,5 +474,5 @@ def test_bin_overflow_paths(cuda_lib, oracle):
     _check_scene(oracle, s, label='bin overflow')
     # two images with different loads: the lists are per image
     s2 = {k: np.concatenate([v, v], axis=0) for k, v in s.items()}
-    s2['faces'][1, 50:] = 0   # image 1: 50 real faces, the rest degenerate
+    s2['faces'][1, 150:] = 0   # image 1: 150 real faces (bin + row list only), the rest degenerate
     _check_scene(oracle, s2, label='bin overflow, two images')
