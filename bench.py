@@ -85,20 +85,41 @@ def bind_to_gpu_numa_node(index):
     H2D / D2H copies about half their rate once several ranks copy at once (SCALE_r01: 40 -> 20 GB/s per GPU at N=8).
     Returns what was done, for the JSON line."""
     info = {'node': None, 'cpus': None}
-    try:
-        bdf = subprocess.run(['nvidia-smi', '-i', str(index), '--query-gpu=pci.bus_id', '--format=csv,noheader'],
-                             capture_output=True, text=True, timeout=20).stdout.strip().lower()
-        if bdf.count(':') == 2 and len(bdf.split(':')[0]) == 8:
-            bdf = bdf[4:]   # sysfs uses a 4-digit PCI domain
-        with open('/sys/bus/pci/devices/%s/numa_node' % bdf) as f:
-            node = int(f.read().strip())
-        if node < 0:
-            return info
+
+    def parse_cpulist(text):
         cpus = set()
-        with open('/sys/devices/system/node/node%d/cpulist' % node) as f:
-            for part in f.read().strip().split(','):
-                lo, _, hi = part.partition('-')
-                cpus.update(range(int(lo), int(hi or lo) + 1))
+        for part in text.strip().split(','):
+            lo, _, hi = part.partition('-')
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        return cpus
+
+    try:
+        cpus, node = None, None
+        # the driver's own view first: the "CPU Affinity" / "NUMA Affinity" columns of `nvidia-smi topo -m`
+        topo = subprocess.run(['nvidia-smi', 'topo', '-m'], capture_output=True, text=True, timeout=30).stdout
+        import re
+        lines = [re.sub(r'\x1b\[[0-9;]*m', '', l) for l in topo.splitlines()]
+        header = next((l for l in lines if 'CPU Affinity' in l), None)
+        row = next((l for l in lines if l.startswith('GPU%d\t' % index) or l.startswith('GPU%d ' % index)), None)
+        if header and row:
+            hcols = [c.strip() for c in header.split('\t')]
+            rcols = [c.strip() for c in row.split('\t')]
+            ci = hcols.index('CPU Affinity')   # the header line starts with an empty cell above the row labels
+            if ci < len(rcols) and rcols[ci]:
+                cpus = parse_cpulist(rcols[ci])
+                ni = ci + 1
+                node = int(rcols[ni]) if ni < len(rcols) and rcols[ni].isdigit() else None
+        if not cpus:   # sysfs: PCI device -> NUMA node -> cpulist
+            bdf = subprocess.run(['nvidia-smi', '-i', str(index), '--query-gpu=pci.bus_id', '--format=csv,noheader'],
+                                 capture_output=True, text=True, timeout=20).stdout.strip().lower()
+            if bdf.count(':') == 2 and len(bdf.split(':')[0]) == 8:
+                bdf = bdf[4:]   # sysfs uses a 4-digit PCI domain
+            with open('/sys/bus/pci/devices/%s/numa_node' % bdf) as f:
+                node = int(f.read().strip())
+            if node < 0:
+                return info
+            with open('/sys/devices/system/node/node%d/cpulist' % node) as f:
+                cpus = parse_cpulist(f.read())
         cpus &= os.sched_getaffinity(0)
         if cpus:
             os.sched_setaffinity(0, cpus)

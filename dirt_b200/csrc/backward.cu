@@ -59,6 +59,10 @@ namespace dirt {
 #ifndef DIRT_BWD_TMA
 #define DIRT_BWD_TMA 1
 #endif
+#ifndef DIRT_BWD_IMAGES
+#define DIRT_BWD_IMAGES 1       // consecutive images a warp walks at its tile position, the next image's halos requested (TMA)
+#endif                          // while the current one is processed.  Measured at cfg3: 1 -> 363 us, 2 / 4 / 8 -> 410 / 408 / 415 us
+                                // (profiles/r02_kbench_pipeline.txt): fewer, longer CTAs lose more than the prefetch wins
 constexpr int TILE = 8;               // backward tile edge: one warp per 8x8 tile, two pixels per lane
 constexpr int HALO_ROWS = TILE + 2;   // 10
 constexpr int HALO_COLS = TILE + 4;   // 12: col-1 .. col+10 (one pixel around for the Scharr taps, two more to the right
@@ -177,10 +181,9 @@ struct BwdSmem {
     static constexpr int IDS_BYTES = HALO_ROWS * IDS_COLS * 4;
     static constexpr int GBUF_BYTES = HALO_ROWS * GB_COLS * 16;
     static constexpr int PX_OFF = 0;
-    // the face-id tile is dead once every lane holds its ids and slots: the G-buffer tile reuses its bytes
     static constexpr int IDS_OFF = (PX_BYTES + 127) / 128 * 128;
-    static constexpr int GBUF_OFF = IDS_OFF;
-    static constexpr int TABLE_OFF = GBUF_OFF + (GBUF_BYTES > IDS_BYTES ? GBUF_BYTES : IDS_BYTES);
+    static constexpr int GBUF_OFF = IDS_OFF + (IDS_BYTES + 127) / 128 * 128;
+    static constexpr int TABLE_OFF = GBUF_OFF + GBUF_BYTES;
     static constexpr int KEYS_OFF = TABLE_OFF + NSLOT * (int)sizeof(SlotRec);
     static constexpr int BAR_OFF = (KEYS_OFF + NSLOT * 4 + 7) / 8 * 8;
     static constexpr int BYTES = (BAR_OFF + 16 + 127) / 128 * 128;
@@ -529,7 +532,37 @@ __global__ void __launch_bounds__(NW * 32, DIRT_BWD_MIN_BLOCKS * DIRT_BWD_WARPS 
         __syncwarp();
     }
 
-    for (int b = blockIdx.z; b < d.B; b += gridDim.z) {
+    // This warp walks DIRT_BWD_IMAGES consecutive images at its tile position.  Their tile flags are fetched together, and
+    // (TMA tiles) the face-id halo of the next flagged image is requested as soon as this image's ids sit in registers,
+    // its pixel halo as soon as this image's Scharr sums are done: the loads of image i+1 fly under the work on image i.
+    const int b_first = blockIdx.z * DIRT_BWD_IMAGES;
+    const int n_img = min(DIRT_BWD_IMAGES, d.B - b_first);
+    unsigned flagmask;
+    {
+        bool f = false;
+        if (lane < n_img) f = tile_flags == nullptr || tile_flags[(size_t)(b_first + lane) * d.tiles + ty * d.tiles_x + (tx >> 1)] != 0;
+        flagmask = __ballot_sync(0xffffffffu, f);
+    }
+    int ids_issued = -1, px_issued = -1;   // image (index in this warp's run) whose halos are already on their way
+    const auto issue_ids = [&](int bi) {
+        if (lane == 0) {
+            fence_proxy_async();
+            mbar_expect_tx(&bars[0], SM::IDS_BYTES);
+            tma_load_3d(ids_tile, &ids_map, tcol0 - 1 - IDS_COL0, trow0 - 1, b_first + bi, &bars[0]);
+        }
+        ids_issued = bi;
+    };
+    const auto issue_px = [&](int bi) {
+        if (lane == 0) {
+            fence_proxy_async();
+            mbar_expect_tx(&bars[1], SM::PX_BYTES);
+            tma_load_3d(tile, &px_map, (tcol0 - 1 - PxTile<C>::COL0) * C, trow0 - 1, b_first + bi, &bars[1]);
+        }
+        px_issued = bi;
+    };
+
+    for (int bi = 0; bi < n_img; ++bi) {
+    const int b = b_first + bi;
     const TriInterp* itp_b = ws.itp + (size_t)b * d.F;
     const TriXY* xy_b = ws.xy + (size_t)b * d.F;
     float* gverts = grad_vertices + (size_t)(per_item ? b : 0) * d.V * 4;
@@ -537,8 +570,11 @@ __global__ void __launch_bounds__(NW * 32, DIRT_BWD_MIN_BLOCKS * DIRT_BWD_WARPS 
     const size_t img = (size_t)b * H * W;
     const size_t p0 = img + (size_t)row0 * W + col;   // pixel 0 of this lane (pixel 1: + W)
     const bool in0 = col < W && row0 < H, in1 = col < W && row0 + 1 < H;
+    // the next flagged image of this warp's run (n_img: none)
+    const unsigned later = flagmask & ~((2u << bi) - 1u);
+    const int nb = later ? __ffs(later) - 1 : n_img;
 
-    // ---- grad_pixels of this lane's pixels: needed on every path, so the loads go out before the tile flag is even read
+    // ---- grad_pixels of this lane's pixels: needed on every path, so the loads go out first
     float gp[2][C];
 #pragma unroll
     for (int pix = 0; pix < 2; ++pix) {
@@ -554,20 +590,13 @@ __global__ void __launch_bounds__(NW * 32, DIRT_BWD_MIN_BLOCKS * DIRT_BWD_WARPS 
             for (int ch = 0; ch < C; ++ch) gp[pix][ch] = __ldg(grad_pixels + p * cs + c0 + ch);
         }
     }
-    const bool flagged = tile_flags == nullptr || tile_flags[(size_t)b * d.tiles + ty * d.tiles_x + (tx >> 1)] != 0;
+    const bool flagged = (flagmask >> bi) & 1u;
 
-    // ---- (1) stage the halo of face ids and pixels ------------------------------------------------------------------
+    // ---- (1) stage the halo of face ids and pixels (unless they were requested while the previous image was processed)
     if (flagged) {
         if (use_tma) {
-            if (lane == 0) {
-                fence_proxy_async();
-                mbar_expect_tx(&bars[0], SM::IDS_BYTES);
-                tma_load_3d(ids_tile, &ids_map, tcol0 - 1 - IDS_COL0, trow0 - 1, b, &bars[0]);
-                if (want_pos) {
-                    mbar_expect_tx(&bars[1], SM::PX_BYTES);
-                    tma_load_3d(tile, &px_map, (tcol0 - 1 - PxTile<C>::COL0) * C, trow0 - 1, b, &bars[1]);
-                }
-            }
+            if (ids_issued != bi) issue_ids(bi);
+            if (want_pos && px_issued != bi) issue_px(bi);
         } else {
             for (int e = lane; e < HALO_ROWS * HALO_COLS; e += 32) {
                 const int hr = e / HALO_COLS, hc = e - hr * HALO_COLS;
@@ -616,16 +645,22 @@ __global__ void __launch_bounds__(NW * 32, DIRT_BWD_MIN_BLOCKS * DIRT_BWD_WARPS 
     const int id0 = ids_tile[i0], id1 = ids_tile[i0 + IDS_COLS], idr = ids_tile[ring_r * IDS_COLS + ring_c + IDS_COL0];
     if (want_col && in0) store_gb(0, id0 < 0);
     if (want_col && in1) store_gb(1, id1 < 0);
+    // neighbours in the visibility buffer (the id tile is about to be handed to the next image)
+    const int up0 = ids_tile[i0 - IDS_COLS], l0 = ids_tile[i0 - 1], r0 = ids_tile[i0 + 1];
+    const int l1 = ids_tile[i0 + IDS_COLS - 1], r1 = ids_tile[i0 + IDS_COLS + 1], dn1 = ids_tile[i0 + 2 * IDS_COLS];
+    __syncwarp();
+    if (use_tma && nb < n_img) issue_ids(nb);
     if (!__any_sync(0xffffffffu, (id0 & id1 & idr) >= 0)) {
         // no face in the tile or its ring
-        if (use_tma && want_pos) { mbar_wait(&bars[1], parity_px); parity_px ^= 1; }
+        if (use_tma && want_pos) {
+            mbar_wait(&bars[1], parity_px); parity_px ^= 1;
+            if (nb < n_img) issue_px(nb);
+        }
         continue;
     }
     // per pixel: covered, or (interior pixels only) a covered 4-neighbour that could dilate into it
     bool near0, near1, interior0 = true, interior1 = true;
     {
-        const int up0 = ids_tile[i0 - IDS_COLS], l0 = ids_tile[i0 - 1], r0 = ids_tile[i0 + 1];
-        const int l1 = ids_tile[i0 + IDS_COLS - 1], r1 = ids_tile[i0 + IDS_COLS + 1], dn1 = ids_tile[i0 + 2 * IDS_COLS];
         if (!inner) {
             interior0 = col > 0 && row0 > 0 && col < W - 1 && row0 < H - 1;
             interior1 = col > 0 && row0 + 1 < H - 1 && col < W - 1;
@@ -659,7 +694,10 @@ __global__ void __launch_bounds__(NW * 32, DIRT_BWD_MIN_BLOCKS * DIRT_BWD_WARPS 
     __syncwarp();
     if (__any_sync(0xffffffffu, overflow)) {
         // more distinct faces than slots: the reference-shaped path for this tile
-        if (use_tma && want_pos) { mbar_wait(&bars[1], parity_px); parity_px ^= 1; }
+        if (use_tma && want_pos) {
+            mbar_wait(&bars[1], parity_px); parity_px ^= 1;
+            if (nb < n_img) issue_px(nb);
+        }
         tile_generic<C>(vertices, pixels, grad_pixels, face_ids, gverts, gcols, itp_b, Frame{d.B, H, W}, d.V, b, col, row0, cs, c0, want_pos, want_col);
         __syncwarp();
         continue;
@@ -827,6 +865,10 @@ __global__ void __launch_bounds__(NW * 32, DIRT_BWD_MIN_BLOCKS * DIRT_BWD_WARPS 
         }
     }
 
+    // the pixel halo has served this image: hand its buffer to the next one while the reduction runs
+    __syncwarp();
+    if (use_tma && want_pos && nb < n_img) issue_px(nb);
+
     // ---- (4) per-face reduction -----------------------------------------------------------------------------------------
     // One iteration per occupied slot: the 3*(C+3) sums of the face are reduced over the 32 lanes with a transposed
     // butterfly (each lane ends up owning one finished sum) and leave the SM as ONE warp-wide RED.  Faces that own only a
@@ -921,7 +963,7 @@ __global__ void __launch_bounds__(NW * 32, DIRT_BWD_MIN_BLOCKS * DIRT_BWD_WARPS 
     }
 #endif
     __syncwarp();   // the next image's staging overwrites the tile buffers
-    }   // b
+    }   // bi
 }
 
 // sum over the batch of per-item rows: out[i] = sum_b in[b * n + i]  (the two-stage form of BWD_SHARED_GEOMETRY)
@@ -982,7 +1024,8 @@ static cudaError_t launch_tile_kernel(const CUtensorMap& px_map, const CUtensorM
         if (e != cudaSuccess) return e;
         configured = true;
     }
-    const dim3 grid((unsigned)((d.btiles_x + NW - 1) / NW), (unsigned)d.btiles_y, (unsigned)min(d.B, 65535));
+    // z: runs of DIRT_BWD_IMAGES consecutive images (a batch beyond 65535 runs would need a second grid dimension)
+    const dim3 grid((unsigned)((d.btiles_x + NW - 1) / NW), (unsigned)d.btiles_y, (unsigned)((d.B + DIRT_BWD_IMAGES - 1) / DIRT_BWD_IMAGES));
     kernel<<<grid, NW * 32, smem, stream>>>(px_map, ids_map, vertices, pixels, grad_pixels, face_ids, grad_background,
                                             grad_vertices, grad_vertex_colors, ws, d, tflags, cs, c0, flags, expect_tag);
     return cudaGetLastError();

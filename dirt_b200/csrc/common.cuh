@@ -18,8 +18,8 @@ constexpr int TILE_H_SHIFT = 3;
 constexpr uint32_t KEY_EMPTY = 0x00800000u; // depth key of the cleared depth buffer (1.0)
 constexpr int SMALL_TILE_LIMIT = 16;       // faces whose bbox spans <= this many tiles are binned per tile;
                                            // larger ones go to the per-image "large" list
-constexpr int BIN_CAP = 64;                // face references a tile's bin holds; further ones go to the image's overflow list
-constexpr int OVF_PER_FACE = 4;            // capacity of an image's overflow list, in entries per face of the image
+constexpr int BIN_CAP = 128;               // face references a tile's bin holds; further ones go to the overflow list of the tile's row
+constexpr int OVF_ROW_CAP = 1024;          // capacity of the overflow list of one row of tiles of one image
 constexpr int MAX_GROUPS = 128;            // channel groups (each 1 or 3 wide)
 
 constexpr uint32_t KIND_CULLED = 0, KIND_SMALL = 1, KIND_HARD = 2, KIND_LARGE = 3;
@@ -95,16 +95,17 @@ struct Workspace {
     TriShade* shade;      // [B*F]  (written by forward calls with C <= SHADE_MAX_CHANNELS)
     // One-pass binning: the setup kernel appends a face to the bin of every tile its bounding box touches
     // (position = atomicAdd on the tile's count).  A bin holds BIN_CAP references at a fixed place, so the raster
-    // kernel fetches a tile's count and its references in ONE hop; what does not fit goes to the image's overflow list
-    // of (tile, face) pairs, and what does not fit there either to the image's large list (scanned by every tile).
+    // kernel fetches a tile's count and its references in ONE hop; what does not fit goes to the overflow list of the
+    // tile's ROW of tiles ((tile, face) pairs, read only by the tiles of that row whose bins were full), and what does
+    // not fit there either to the image's large list (scanned by every tile).
     int* tile_count;      // [B*T]  references binned to the tile (may exceed BIN_CAP: the excess is in the overflow list)
     unsigned char* tile_flags;  // [B*T]  1 if the 16x8 tile or one of its 8 neighbours shows a face (written by the raster kernel)
     unsigned char* face_in_large;  // [B*F]  the face already sits in the large list (last-resort path only)
     int* large_count;     // [B]
-    int* ovf_count;       // [B]
+    int* ovf_count;       // [B*tiles_y]
     int* large_list;      // [B*F]   faces spanning > SMALL_TILE_LIMIT tiles, hard faces
     int* bins;            // [B*T*BIN_CAP]
-    int2* ovf;            // [B*OVF_PER_FACE*F]  (tile, face)
+    int2* ovf;            // [B*tiles_y*OVF_ROW_CAP]  (tile, face)
     struct Header* header; // identity of the (vertices, faces, sizes) the setup records belong to; error flag
     int32_t* face_ids;    // [B*H*W] (used when the caller does not supply a buffer)
     size_t zero_bytes;    // bytes from tile_count that the forward pass zeroes (counts, flags, list counts, header)
@@ -130,12 +131,13 @@ inline Workspace carve_workspace(void* base, int B, int H, int W, int F)
     ws.tile_flags = (unsigned char*)take(BT);
     ws.face_in_large = (unsigned char*)take(BF);
     ws.large_count = (int*)take((size_t)B * sizeof(int));
-    ws.ovf_count = (int*)take((size_t)B * sizeof(int));
+    const size_t rows = (size_t)B * ((H + TILE_H - 1) / TILE_H);
+    ws.ovf_count = (int*)take(rows * sizeof(int));
     ws.header = (Header*)take(256);
     ws.zero_bytes = (size_t)((p + off) - (char*)ws.tile_count);
     ws.large_list = (int*)take(BF * sizeof(int));
     ws.bins = (int*)take(BT * BIN_CAP * sizeof(int));
-    ws.ovf = (int2*)take(BF * OVF_PER_FACE * sizeof(int2));
+    ws.ovf = (int2*)take(rows * OVF_ROW_CAP * sizeof(int2));
     ws.face_ids = (int32_t*)take((size_t)B * H * W * sizeof(int32_t));
     ws.bytes = off;
     return ws;

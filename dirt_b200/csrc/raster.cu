@@ -407,10 +407,11 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, DIRT_RASTER_MIN_BLOCKS) 
     if (nbin > 0)
         consume_list<true, false>(ws.bins + ((size_t)b * d.tiles + t) * BIN_CAP, min(nbin, BIN_CAP), 0, cov_b, itp_b, verts,
                                   slots_all[warp], lane, tcol0, trow0, d.H, d.W, quad, tile_max);
-    if (nbin > BIN_CAP)   // the bin was full: this tile's share of the image's overflow list
-        consume_list<true, true>(reinterpret_cast<const int*>(ws.ovf + (size_t)b * OVF_PER_FACE * d.F),
-                                 min(ws.ovf_count[b], OVF_PER_FACE * d.F), t, cov_b, itp_b, verts, slots_all[warp], lane,
-                                 tcol0, trow0, d.H, d.W, quad, tile_max);
+    if (nbin > BIN_CAP) {   // the bin was full: this tile's share of its row's overflow list
+        const size_t orow = (size_t)b * d.tiles_y + ty;
+        consume_list<true, true>(reinterpret_cast<const int*>(ws.ovf + orow * OVF_ROW_CAP), min(ws.ovf_count[orow], OVF_ROW_CAP), t,
+                                 cov_b, itp_b, verts, slots_all[warp], lane, tcol0, trow0, d.H, d.W, quad, tile_max);
+    }
     if (nlarge > 0)
         consume_list<false, false>(ws.large_list + (size_t)b * d.F, nlarge, 0, cov_b, itp_b, verts, slots_all[warp], lane, tcol0,
                                    trow0, d.H, d.W, quad, tile_max);

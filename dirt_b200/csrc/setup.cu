@@ -209,25 +209,43 @@ __global__ void __launch_bounds__(DIRT_SETUP_THREADS, DIRT_SETUP_MIN_BLOCKS) set
     };
     if (small) {
         int* counts = ws.tile_count + (size_t)b * d.tiles;
-        for (int ty = ty0; ty <= ty1; ++ty)
-            for (int tx = tx0; tx <= tx1; ++tx) {
-                const int t = ty * d.tiles_x + tx;
-                const int pos = atomicAdd(&counts[t], 1);
-                if (pos < BIN_CAP) {
-                    ws.bins[((size_t)b * d.tiles + t) * BIN_CAP + pos] = f;
-                } else {
-                    // the tile's bin is full: the image's overflow list, and if that is full as well the large list
-                    // (a face that sits in both a bin and the large list is tested twice, which cannot change a minimum)
-                    const int q = atomicAdd(&ws.ovf_count[b], 1);
-                    if (q < OVF_PER_FACE * d.F) ws.ovf[(size_t)b * OVF_PER_FACE * d.F + q] = make_int2(t, f);
-                    else {
-                        // one byte per face, claimed with an atomic OR on the word holding it
-                        unsigned int* word = reinterpret_cast<unsigned int*>(ws.face_in_large) + (gid >> 2);
-                        const unsigned int bit = 1u << (8 * (unsigned)(gid & 3));
-                        if ((atomicOr(word, bit) & bit) == 0u) to_large_list();
-                    }
+        const auto place = [&](int t, int pos) {
+            if (pos < BIN_CAP) {
+                ws.bins[((size_t)b * d.tiles + t) * BIN_CAP + pos] = f;
+            } else {
+                // the tile's bin is full: the overflow list of its row of tiles, and if that is full as well the large list
+                // (a face that sits in both a bin and the large list is tested twice, which cannot change a minimum)
+                const size_t row = (size_t)b * d.tiles_y + t / d.tiles_x;
+                const int q = atomicAdd(&ws.ovf_count[row], 1);
+                if (q < OVF_ROW_CAP) ws.ovf[row * OVF_ROW_CAP + q] = make_int2(t, f);
+                else {
+                    // one byte per face, claimed with an atomic OR on the word holding it
+                    unsigned int* word = reinterpret_cast<unsigned int*>(ws.face_in_large) + (gid >> 2);
+                    const unsigned int bit = 1u << (8 * (unsigned)(gid & 3));
+                    if ((atomicOr(word, bit) & bit) == 0u) to_large_list();
                 }
             }
+        };
+        if (tx1 - tx0 <= 1 && ty1 - ty0 <= 1) {
+            // at most 2x2 tiles (nearly every face of a fine mesh): the position-returning atomics go out together, so the
+            // thread waits for one round trip instead of up to four in a row
+            const int t00 = ty0 * d.tiles_x + tx0, t01 = ty0 * d.tiles_x + tx1, t10 = ty1 * d.tiles_x + tx0, t11 = ty1 * d.tiles_x + tx1;
+            const bool two_x = tx1 > tx0, two_y = ty1 > ty0;
+            const int p00 = atomicAdd(&counts[t00], 1);
+            const int p01 = two_x ? atomicAdd(&counts[t01], 1) : 0;
+            const int p10 = two_y ? atomicAdd(&counts[t10], 1) : 0;
+            const int p11 = (two_x && two_y) ? atomicAdd(&counts[t11], 1) : 0;
+            place(t00, p00);
+            if (two_x) place(t01, p01);
+            if (two_y) place(t10, p10);
+            if (two_x && two_y) place(t11, p11);
+        } else {
+            for (int ty = ty0; ty <= ty1; ++ty)
+                for (int tx = tx0; tx <= tx1; ++tx) {
+                    const int t = ty * d.tiles_x + tx;
+                    place(t, atomicAdd(&counts[t], 1));
+                }
+        }
     } else {
         to_large_list();
     }
