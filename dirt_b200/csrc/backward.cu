@@ -45,7 +45,8 @@ namespace dirt {
 #define DIRT_ABLATE 0   // timing experiments only: 1 = no per-face reduction, 2 = no Scharr/dilation, 3 = both
 #endif
 #ifndef DIRT_BWD_SMALL_FACE
-#define DIRT_BWD_SMALL_FACE 12  // faces owning at most this many records in a tile are added directly (0: always reduce)
+#define DIRT_BWD_SMALL_FACE 20  // faces owning at most this many records in a tile are added directly (0: always reduce);
+                                // 12 / 20 / 32: 389.5 / 385.5 / 429 us at cfg3 (profiles/r02_kbench_tma_variants.txt, _ablation_notma.txt)
 #endif
 #ifndef DIRT_BWD_MIN_BLOCKS
 #define DIRT_BWD_MIN_BLOCKS 8   // x 4 warps: <= 64 registers
@@ -493,7 +494,11 @@ __global__ void __launch_bounds__(NW * 32, DIRT_BWD_MIN_BLOCKS * DIRT_BWD_WARPS 
     extern __shared__ __align__(128) unsigned char smem_raw[];
 
     // grid: x = groups of NW tiles along a tile row, y = tile row, z = image
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // The warp index goes through a warp reduction so that the compiler KNOWS it (and the tile coordinates, the TMA /
+    // border / right-edge predicates derived from it) to be warp-uniform: branches on them stay convergent and the
+    // shuffles of the reduction need no re-convergence barriers.
+    const int lane = threadIdx.x & 31;
+    const int warp = (int)__reduce_min_sync(0xffffffffu, threadIdx.x >> 5);
     const int tx = blockIdx.x * NW + warp, ty = blockIdx.y;
     if (tx >= d.btiles_x) return;
     unsigned char* const sm = smem_raw + warp * SM::BYTES;
@@ -882,15 +887,15 @@ __global__ void __launch_bounds__(NW * 32, DIRT_BWD_MIN_BLOCKS * DIRT_BWD_WARPS 
         const int owner_stride = (owner & 16) ? 4 : (C == 4 ? 4 : cs);
         const int kc0 = term[0].key_col, kc1 = term[1].key_col, kp0 = term[0].key_pos, kp1 = term[1].key_pos;
         unsigned direct = 0;   // bit 0/1: colour record of pixel 0/1, bit 2/3: position record of pixel 0/1
-        unsigned occupied = __ballot_sync(0xffffffffu, lane < NSLOT && keys[lane] >= 0);
+        // slots that own at least one record of this tile (faces of the ring that nothing dilates from own none)
+        unsigned occupied = __reduce_or_sync(0xffffffffu, (kc0 >= 0 ? 1u << kc0 : 0u) | (kc1 >= 0 ? 1u << kc1 : 0u) |
+                                                              (kp0 >= 0 ? 1u << kp0 : 0u) | (kp1 >= 0 ? 1u << kp1 : 0u));
         while (occupied) {
             const int s = __ffs(occupied) - 1;
             occupied &= occupied - 1;
             const bool mc0 = kc0 == s, mc1 = kc1 == s, mp0 = kp0 == s, mp1 = kp1 == s;
-            const int records = __popc(__ballot_sync(0xffffffffu, mc0)) + __popc(__ballot_sync(0xffffffffu, mc1)) +
-                                __popc(__ballot_sync(0xffffffffu, mp0)) + __popc(__ballot_sync(0xffffffffu, mp1));
-            if (records == 0) continue;   // a face of the ring that nothing dilates from
 #if DIRT_BWD_SMALL_FACE > 0
+            const unsigned records = __reduce_add_sync(0xffffffffu, (unsigned)mc0 + (unsigned)mc1 + (unsigned)mp0 + (unsigned)mp1);
             if (records <= DIRT_BWD_SMALL_FACE) {
                 direct |= (mc0 ? 1u : 0u) | (mc1 ? 2u : 0u) | (mp0 ? 4u : 0u) | (mp1 ? 8u : 0u);
                 continue;

@@ -292,7 +292,8 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, DIRT_RASTER_MIN_BLOCKS) 
 {
     __shared__ Slot slots_all[WARPS_PER_BLOCK][32];
     // grid: x = groups of WARPS_PER_BLOCK * TILES_PER_WARP tiles along a tile row, y = tile row, z = image
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int lane = threadIdx.x & 31;
+    const int warp = (WARPS_PER_BLOCK == 1) ? 0 : (int)__reduce_min_sync(0xffffffffu, threadIdx.x >> 5);   // known to be warp-uniform
     const int txb = (blockIdx.x * WARPS_PER_BLOCK + warp) * TILES_PER_WARP, ty = blockIdx.y;
     if (txb >= d.tiles_x) return;
     const int trow0 = ty * TILE_H;
