@@ -80,7 +80,7 @@ static bool shape_ok(int B, int H, int W, int C, int V, int F)
 extern "C" size_t dirt_workspace_bytes(int B, int H, int W, int C, int V, int F)
 {
     if (!shape_ok(B, H, W, C > 0 ? C : 1, V, F)) return 0;
-    Workspace ws = carve_workspace(nullptr, B, H, W, F);
+    Workspace ws = carve_workspace(nullptr, B, H, W, C, V, F);
     return ws.bytes + 256;
 }
 
@@ -142,7 +142,7 @@ extern "C" int dirt_rasterise_forward(const float* background, const float* vert
     int rc = check_workspace(workspace, workspace_bytes, B, H, W, C, V, F);
     if (rc != DIRT_OK) return rc;
     cudaStream_t stream = (cudaStream_t)cuda_stream;
-    const Workspace ws = carve_workspace(workspace, B, H, W, F);
+    const Workspace ws = carve_workspace(workspace, B, H, W, C, V, F);
     const Dims d = make_dims(B, H, W, C, V, F);
     CUDA_TRY(launch_setup_and_bin(vertices, faces, vertex_colors, ws, d, stream, &launches));
     CUDA_TRY(launch_raster_forward(vertices, background, vertex_colors, pixels, face_ids_out, ws, d, stream, &launches));
@@ -164,7 +164,7 @@ extern "C" int dirt_rasterise_visibility(const float* vertices, const int32_t* f
     int rc = check_workspace(workspace, workspace_bytes, B, H, W, 1, V, F);
     if (rc != DIRT_OK) return rc;
     cudaStream_t stream = (cudaStream_t)cuda_stream;
-    const Workspace ws = carve_workspace(workspace, B, H, W, F);
+    const Workspace ws = carve_workspace(workspace, B, H, W, 1, V, F);
     const Dims d = make_dims(B, H, W, 1, V, F);
     CUDA_TRY(launch_setup_and_bin(vertices, faces, nullptr, ws, d, stream, &launches));
     CUDA_TRY(launch_raster_visibility(vertices, face_ids, gbuffer, ws, d, stream, &launches));
@@ -197,7 +197,7 @@ static int backward_impl(const float* vertices, const int32_t* faces, const floa
     rc = check_workspace(workspace, workspace_bytes, B, H, W, C, V, F);
     if (rc != DIRT_OK) return rc;
     cudaStream_t stream = (cudaStream_t)cuda_stream;
-    const Workspace ws = carve_workspace(workspace, B, H, W, F);
+    const Workspace ws = carve_workspace(workspace, B, H, W, C, V, F);
     const Dims d = make_dims(B, H, W, C, V, F);
     const int32_t* ids = face_ids;
     // the tile coverage flags in the workspace describe `ids` when the raster kernel that produced them ran on this workspace
@@ -247,7 +247,7 @@ extern "C" int dirt_workspace_status(const void* workspace, size_t workspace_byt
     if (B == 0) return DIRT_OK;
     int rc = check_workspace(const_cast<void*>(workspace), workspace_bytes, B, H, W, C, V, F);
     if (rc != DIRT_OK) return rc;
-    const Workspace ws = carve_workspace(const_cast<void*>(workspace), B, H, W, F);
+    const Workspace ws = carve_workspace(const_cast<void*>(workspace), B, H, W, C, V, F);
     Header h;
     cudaStream_t stream = (cudaStream_t)cuda_stream;
     if (cudaMemcpyAsync(&h, ws.header, sizeof(h), cudaMemcpyDeviceToHost, stream) != cudaSuccess) return DIRT_ERR_CUDA;

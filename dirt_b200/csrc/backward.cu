@@ -368,7 +368,7 @@ __device__ __noinline__ void tile_generic(const float* __restrict__ vertices, co
                                           const float* __restrict__ grad_pixels, const int32_t* __restrict__ face_ids,
                                           float* __restrict__ gverts, float* __restrict__ gcols,   // rows of this image (or the shared rows); gcols at the group's first channel
                                           const TriInterp* __restrict__ itp_b, const Frame d, int V, int b, int col, int row0, int cs, int c0,
-                                          bool want_pos, bool want_col)
+                                          int gstride, bool want_pos, bool want_col)
 {
     constexpr int N0 = (C == 1) ? 1 : 3;
     constexpr int NG = (C == 4) ? 2 : 1;
@@ -391,7 +391,7 @@ __device__ __noinline__ void tile_generic(const float* __restrict__ vertices, co
             for (int ch = 0; want_col && ch < C; ++ch) {
                 const float gp = __ldg(&grad_pixels[p * cs + c0 + ch]);
 #pragma unroll
-                for (int k = 0; k < 3; ++k) atomicAdd(&gcols[(size_t)vid[k] * cs + ch], gp * bary[k]);
+                for (int k = 0; k < 3; ++k) atomicAdd(&gcols[(size_t)vid[k] * gstride + ch], gp * bary[k]);
             }
         }
         const bool interior = col > 0 && row > 0 && col < d.W - 1 && row < d.H - 1;
@@ -482,6 +482,7 @@ __global__ void __launch_bounds__(NW * 32, DIRT_BWD_MIN_BLOCKS * DIRT_BWD_WARPS 
     const int32_t* __restrict__ face_ids, float* __restrict__ grad_background, float* __restrict__ grad_vertices,
     float* __restrict__ grad_vertex_colors, Workspace ws, Dims d, const unsigned char* __restrict__ tile_flags,
     int cs, int c0,   // cs: channels per pixel in the tensors, c0: first channel of the group this launch handles (width C)
+    int gstride,      // floats per vertex row of grad_vertex_colors as this launch sees it (cs, or 4 for the padded rows of C = 3)
     int flags,        // BWD_SHARED_GEOMETRY: vertex gradients accumulated over the batch ([V,.]); BWD_SKIP_POSITION / _COLOUR
     unsigned long long expect_tag)   // != 0: the caller promised that the workspace holds the setup records with this tag
 {
@@ -571,7 +572,7 @@ __global__ void __launch_bounds__(NW * 32, DIRT_BWD_MIN_BLOCKS * DIRT_BWD_WARPS 
     const TriInterp* itp_b = ws.itp + (size_t)b * d.F;
     const TriXY* xy_b = ws.xy + (size_t)b * d.F;
     float* gverts = grad_vertices + (size_t)(per_item ? b : 0) * d.V * 4;
-    float* gcols = grad_vertex_colors + (size_t)(per_item ? b : 0) * d.V * cs + c0;
+    float* gcols = grad_vertex_colors + (size_t)(per_item ? b : 0) * d.V * gstride + c0;
     const size_t img = (size_t)b * H * W;
     const size_t p0 = img + (size_t)row0 * W + col;   // pixel 0 of this lane (pixel 1: + W)
     const bool in0 = col < W && row0 < H, in1 = col < W && row0 + 1 < H;
@@ -703,7 +704,7 @@ __global__ void __launch_bounds__(NW * 32, DIRT_BWD_MIN_BLOCKS * DIRT_BWD_WARPS 
             mbar_wait(&bars[1], parity_px); parity_px ^= 1;
             if (nb < n_img) issue_px(nb);
         }
-        tile_generic<C>(vertices, pixels, grad_pixels, face_ids, gverts, gcols, itp_b, Frame{d.B, H, W}, d.V, b, col, row0, cs, c0, want_pos, want_col);
+        tile_generic<C>(vertices, pixels, grad_pixels, face_ids, gverts, gcols, itp_b, Frame{d.B, H, W}, d.V, b, col, row0, cs, c0, gstride, want_pos, want_col);
         __syncwarp();
         continue;
     }
@@ -884,7 +885,7 @@ __global__ void __launch_bounds__(NW * 32, DIRT_BWD_MIN_BLOCKS * DIRT_BWD_WARPS 
         const int owner = owner_meta<C>(lane);
         // destination of this lane's finished sum: component (owner >> 2) & 3 of row `vid` of grad_vertices / grad_vertex_colors
         float* const owner_row = ((owner & 16) ? gverts : gcols) + ((owner >> 2) & 3);
-        const int owner_stride = (owner & 16) ? 4 : (C == 4 ? 4 : cs);
+        const int owner_stride = (owner & 16) ? 4 : (C == 4 ? 4 : gstride);
         const int kc0 = term[0].key_col, kc1 = term[1].key_col, kp0 = term[0].key_pos, kp1 = term[1].key_pos;
         unsigned direct = 0;   // bit 0/1: colour record of pixel 0/1, bit 2/3: position record of pixel 0/1
         // slots that own at least one record of this tile (faces of the ring that nothing dilates from own none)
@@ -954,9 +955,10 @@ __global__ void __launch_bounds__(NW * 32, DIRT_BWD_MIN_BLOCKS * DIRT_BWD_WARPS 
                 for (int k = 0; k < 3; ++k) {
                     if (colour) {
                         if (C == 4) red_add_v4(gcols + (size_t)vid[k] * 4, w[k] * sc[pix][0], w[k] * sc[pix][1 % NS], w[k] * sc[pix][2 % NS], w[k] * sc[pix][3 % NS]);
+                        else if (C == 3 && gstride == 4) red_add_v4(gcols + (size_t)vid[k] * 4, w[k] * sc[pix][0], w[k] * sc[pix][1 % NS], w[k] * sc[pix][2 % NS], 0.f);
                         else {
 #pragma unroll
-                            for (int j = 0; j < C; ++j) atomicAdd(gcols + (size_t)vid[k] * cs + j, w[k] * sc[pix][j]);
+                            for (int j = 0; j < C; ++j) atomicAdd(gcols + (size_t)vid[k] * gstride + j, w[k] * sc[pix][j]);
                         }
                     } else {
                         red_add_v4(gverts + (size_t)vid[k] * 4, w[k] * sc[pix][C], w[k] * sc[pix][C + 1], 0.f, w[k] * sc[pix][C + 2]);
@@ -971,19 +973,15 @@ __global__ void __launch_bounds__(NW * 32, DIRT_BWD_MIN_BLOCKS * DIRT_BWD_WARPS 
     }   // bi
 }
 
-// sum over the batch of per-item rows: out[i] = sum_b in[b * n + i]  (the two-stage form of BWD_SHARED_GEOMETRY)
-__global__ void __launch_bounds__(256) batch_sum_kernel(const float* __restrict__ in, float* __restrict__ out, int n, int B)
+// grad_vertex_colors of a 3-channel launch is accumulated in 16-byte rows (one vector RED per vertex instead of three
+// scalar ones) and brought to its [.,3] layout afterwards
+__global__ void __launch_bounds__(256) unpad_rows_kernel(const float* __restrict__ in, float* __restrict__ out, long long rows)
 {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    float acc = 0.f;
-    for (int b = 0; b < B; ++b) acc += in[(size_t)b * n + i];
-    out[i] = acc;
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // one output element
+    if (i >= rows * 3) return;
+    const long long r = i / 3;
+    out[i] = in[r * 4 + (i - r * 3)];
 }
-
-#ifndef DIRT_BWD_SHARED_TWO_STAGE
-#define DIRT_BWD_SHARED_TWO_STAGE 0   // 1: accumulate per item into scratch, then one summing pass (instead of atomics on [V,.])
-#endif
 
 // ---- host side --------------------------------------------------------------------------------------------------------
 static PFN_cuTensorMapEncodeTiled tensor_map_encoder()
@@ -1016,7 +1014,7 @@ static cudaError_t launch_tile_kernel(const CUtensorMap& px_map, const CUtensorM
                                       const float* pixels, const float* grad_pixels, const int32_t* face_ids,
                                       float* grad_background, float* grad_vertices, float* grad_vertex_colors,
                                       const Workspace& ws, const Dims& d, const unsigned char* tflags, int cs, int c0,
-                                      int flags, unsigned long long expect_tag, cudaStream_t stream)
+                                      int gstride, int flags, unsigned long long expect_tag, cudaStream_t stream)
 {
     constexpr int NW = DIRT_BWD_WARPS;
     auto kernel = backward_tile_kernel<C, NSLOT, NW, USE_TMA>;
@@ -1032,7 +1030,7 @@ static cudaError_t launch_tile_kernel(const CUtensorMap& px_map, const CUtensorM
     // z: runs of DIRT_BWD_IMAGES consecutive images (a batch beyond 65535 runs would need a second grid dimension)
     const dim3 grid((unsigned)((d.btiles_x + NW - 1) / NW), (unsigned)d.btiles_y, (unsigned)((d.B + DIRT_BWD_IMAGES - 1) / DIRT_BWD_IMAGES));
     kernel<<<grid, NW * 32, smem, stream>>>(px_map, ids_map, vertices, pixels, grad_pixels, face_ids, grad_background,
-                                            grad_vertices, grad_vertex_colors, ws, d, tflags, cs, c0, flags, expect_tag);
+                                            grad_vertices, grad_vertex_colors, ws, d, tflags, cs, c0, gstride, flags, expect_tag);
     return cudaGetLastError();
 }
 
@@ -1042,33 +1040,23 @@ cudaError_t launch_backward(const float* vertices, const float* pixels, const fl
                             bool tile_flags_valid, int flags, unsigned long long expect_tag, cudaStream_t stream, int* launches)
 {
     cudaError_t e;
-    // two-stage form of the batch accumulation: per-item rows in scratch (the workspace's own face-id block, free when
-    // the caller supplied the ids), then one summing pass
-    float* out_gv = grad_vertices;
-    float* out_gc = grad_vertex_colors;
-    bool two_stage = false;
-#if DIRT_BWD_SHARED_TWO_STAGE
-    if ((flags & BWD_SHARED_GEOMETRY) && face_ids != ws.face_ids && d.B > 1 &&
-        (size_t)d.B * d.V * (4 + d.C) <= (size_t)d.B * d.H * d.W) {
-        two_stage = true;
-        grad_vertices = reinterpret_cast<float*>(ws.face_ids);
-        grad_vertex_colors = grad_vertices + (size_t)d.B * d.V * 4;
-        flags &= ~BWD_SHARED_GEOMETRY;
-    }
-#endif
     const size_t rows = (size_t)((flags & BWD_SHARED_GEOMETRY) ? 1 : d.B) * d.V;
-    if ((e = cudaMemsetAsync(grad_vertices, 0, sizeof(float) * rows * (two_stage ? 4 + d.C : 4), stream)) != cudaSuccess) return e;
-    if (!two_stage && (e = cudaMemsetAsync(grad_vertex_colors, 0, sizeof(float) * rows * d.C, stream)) != cudaSuccess) return e;
+    // C = 3 as one group: colour gradients go to padded rows in the workspace (see unpad_rows_kernel)
+    const bool padded = d.C == 3 && groups.n == 1 && ws.gc_pad != nullptr && rows > 0;
+    float* const gc_out = grad_vertex_colors;
+    if (padded) grad_vertex_colors = ws.gc_pad;
+    const int gstride = padded ? 4 : d.C;
+    if ((e = cudaMemsetAsync(grad_vertices, 0, sizeof(float) * rows * 4, stream)) != cudaSuccess) return e;
+    if ((e = cudaMemsetAsync(grad_vertex_colors, 0, sizeof(float) * rows * gstride, stream)) != cudaSuccess) return e;
     const auto finish = [&]() -> cudaError_t {
-        if (!two_stage) return cudaSuccess;
-        const int n4 = d.V * 4, nc = d.V * d.C;
-        batch_sum_kernel<<<(n4 + 255) / 256, 256, 0, stream>>>(grad_vertices, out_gv, n4, d.B);
-        batch_sum_kernel<<<(nc + 255) / 256, 256, 0, stream>>>(grad_vertex_colors, out_gc, nc, d.B);
-        *launches += 2;
+        if (!padded) return cudaSuccess;
+        const long long n = (long long)rows * 3;
+        unpad_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(grad_vertex_colors, gc_out, (long long)rows);
+        ++*launches;
         return cudaGetLastError();
     };
     const long long total_tiles = (long long)d.B * d.btiles;
-    if (total_tiles == 0) return cudaSuccess;
+    if (total_tiles == 0) return finish();
     ScopedKernelTimer timer(2, stream);
     // C == 4 with the default grouping {3,1} and 16-byte aligned tensors: one fused launch.  Everything else: one launch
     // per channel group (width 3 or 1) on its slice of the channels -- what the reference does at the Python level
@@ -1089,9 +1077,9 @@ cudaError_t launch_backward(const float* vertices, const float* pixels, const fl
               make_tile_map(&ids_map, face_ids, CU_TENSOR_MAP_DATA_TYPE_INT32, d.B, d.H, d.W, 1, IDS_COLS);
 #define DIRT_LAUNCH(CC, NSLOT, c0)                                                                                             \
     (tma ? launch_tile_kernel<CC, NSLOT, true>(px_map, ids_map, vertices, pixels, grad_pixels, face_ids, grad_background,       \
-                                               grad_vertices, grad_vertex_colors, ws, d, tflags, d.C, c0, flags, expect_tag, stream)               \
+                                               grad_vertices, grad_vertex_colors, ws, d, tflags, d.C, c0, gstride, flags, expect_tag, stream)      \
          : launch_tile_kernel<CC, NSLOT, false>(px_map, ids_map, vertices, pixels, grad_pixels, face_ids, grad_background,      \
-                                                grad_vertices, grad_vertex_colors, ws, d, tflags, d.C, c0, flags, expect_tag, stream))
+                                                grad_vertices, grad_vertex_colors, ws, d, tflags, d.C, c0, gstride, flags, expect_tag, stream))
     if (fused4) {
         ++*launches;
         const cudaError_t le = DIRT_LAUNCH(4, DIRT_BWD_SLOTS_C4, 0);

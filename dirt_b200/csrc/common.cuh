@@ -108,13 +108,14 @@ struct Workspace {
     int2* ovf;            // [B*tiles_y*OVF_ROW_CAP]  (tile, face)
     struct Header* header; // identity of the (vertices, faces, sizes) the setup records belong to; error flag
     int32_t* face_ids;    // [B*H*W] (used when the caller does not supply a buffer)
+    float* gc_pad;        // [B*V*4] (C == 3 only) grad_vertex_colors accumulated in 16-byte rows: one vector RED per vertex
     size_t zero_bytes;    // bytes from tile_count that the forward pass zeroes (counts, flags, list counts, header)
     size_t bytes;
 };
 
 __host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
-inline Workspace carve_workspace(void* base, int B, int H, int W, int F)
+inline Workspace carve_workspace(void* base, int B, int H, int W, int C, int V, int F)
 {
     Workspace ws;
     const size_t tiles = (size_t)((W + TILE_W - 1) / TILE_W) * ((H + TILE_H - 1) / TILE_H);
@@ -139,6 +140,7 @@ inline Workspace carve_workspace(void* base, int B, int H, int W, int F)
     ws.bins = (int*)take(BT * BIN_CAP * sizeof(int));
     ws.ovf = (int2*)take(rows * OVF_ROW_CAP * sizeof(int2));
     ws.face_ids = (int32_t*)take((size_t)B * H * W * sizeof(int32_t));
+    ws.gc_pad = (float*)take(C == 3 ? (size_t)B * V * 4 * sizeof(float) : 0);
     ws.bytes = off;
     return ws;
 }

@@ -43,7 +43,11 @@ def _ptr(t):
 
 def _workspace(B, H, W, C, V, F, device):
     nbytes = _lib.lib().dirt_workspace_bytes(B, H, W, C, V, F)
-    return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device), int(nbytes)
+    # the allocation also covers a 3-channel call on the same geometry (its workspace carries padded gradient rows at
+    # the end, everything before is laid out independently of C): deferred shading hands the G-buffer pass's workspace
+    # to the backward call on the shaded, usually 3-channel, image
+    alloc = max(int(nbytes), int(_lib.lib().dirt_workspace_bytes(B, H, W, 3, V, F)), 256)
+    return torch.empty(alloc, dtype=torch.uint8, device=device), int(nbytes)
 
 
 def _require_cuda(*tensors):

@@ -8,7 +8,7 @@ O=gpurun_out
 mkdir -p $O
 for WL in cfg3 cfg5; do
   B=""; [ $WL = cfg5 ] && B="--batch 16"
-  timeout 900 ncu --set full --clock-control none --import-source on -k regex:'raster_kernel|backward_tile' -s 6 -c 2 \
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:'setup_kernel|raster_kernel|backward_tile' -s 9 -c 3 \
       -o $O/prof_${T}_$WL -f python bench.py --workload $WL $B --steps 2 --warmup 3 --no-e2e --no-cpu-baseline --no-graph > $O/prof_${T}_$WL.log 2>&1
   ncu -i $O/prof_${T}_$WL.ncu-rep --page raw --csv > $O/prof_${T}_${WL}_raw.csv 2>/dev/null
   ncu -i $O/prof_${T}_$WL.ncu-rep --page source --csv --print-source cuda,sass -k regex:raster > $O/src_raster_${T}_$WL.csv 2>/dev/null
