@@ -955,7 +955,7 @@ __global__ void __launch_bounds__(NW * 32, DIRT_BWD_MIN_BLOCKS * DIRT_BWD_WARPS 
                 for (int k = 0; k < 3; ++k) {
                     if (colour) {
                         if (C == 4) red_add_v4(gcols + (size_t)vid[k] * 4, w[k] * sc[pix][0], w[k] * sc[pix][1 % NS], w[k] * sc[pix][2 % NS], w[k] * sc[pix][3 % NS]);
-                        else if (C == 3 && gstride == 4) red_add_v4(gcols + (size_t)vid[k] * 4, w[k] * sc[pix][0], w[k] * sc[pix][1 % NS], w[k] * sc[pix][2 % NS], 0.f);
+                        else if (C == 3 && cs == 3 && gstride == 4) red_add_v4(gcols + (size_t)vid[k] * 4, w[k] * sc[pix][0], w[k] * sc[pix][1 % NS], w[k] * sc[pix][2 % NS], 0.f);
                         else {
 #pragma unroll
                             for (int j = 0; j < C; ++j) atomicAdd(gcols + (size_t)vid[k] * gstride + j, w[k] * sc[pix][j]);
