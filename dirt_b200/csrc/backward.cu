@@ -60,6 +60,9 @@ namespace dirt {
 #ifndef DIRT_BWD_TMA
 #define DIRT_BWD_TMA 1
 #endif
+#ifndef DIRT_BWD_SPLIT
+#define DIRT_BWD_SPLIT 0        // 1: tiles no face can reach are copied (grad_background = grad_pixels) by a streaming kernel of
+#endif                          // their own; the tile kernel then only checks their flag
 #ifndef DIRT_BWD_IMAGES
 #define DIRT_BWD_IMAGES 1       // consecutive images a warp walks at its tile position, the next image's halos requested (TMA)
 #endif                          // while the current one is processed.  Measured at cfg3: 1 -> 363 us, 2 / 4 / 8 -> 410 / 408 / 415 us
@@ -452,6 +455,35 @@ __device__ __noinline__ void tile_generic(const float* __restrict__ vertices, co
     }
 }
 
+// grad_background = grad_pixels on whole 16x8 tiles that the forward pass left unflagged (no face on them or next to
+// them), all channels at once: one warp per tile, every lane's copies in flight together.  VEC = float4 per tile row.
+template <int VEC>
+__global__ void __launch_bounds__(128) background_copy_kernel(const float4* __restrict__ grad_pixels, float4* __restrict__ grad_background,
+                                                              const unsigned char* __restrict__ tile_flags, Dims d)
+{
+    const int lane = threadIdx.x & 31;
+    const int tx = blockIdx.x * 4 + (int)__reduce_min_sync(0xffffffffu, threadIdx.x >> 5), ty = blockIdx.y, b = blockIdx.z;
+    if (tx >= d.tiles_x) return;
+    if ((tx + 1) * TILE_W > d.W || (ty + 1) * TILE_H > d.H) return;   // partial tiles stay with the tile kernel
+    if (tile_flags[(size_t)b * d.tiles + ty * d.tiles_x + tx] != 0) return;
+    // a tile row is TILE_W pixels = VEC float4 (VEC = 4 * C for... see the launcher); row pitch in float4 = W * C / 4
+    const size_t pitch = (size_t)d.W * VEC / TILE_W;
+    const size_t base = ((size_t)b * d.H + (size_t)ty * TILE_H) * pitch + (size_t)tx * VEC;
+    constexpr int TOTAL = VEC * TILE_H;            // float4 per tile
+    constexpr int PER_LANE = (TOTAL + 31) / 32;
+    float4 v[PER_LANE];
+#pragma unroll
+    for (int i = 0; i < PER_LANE; ++i) {
+        const int e = i * 32 + lane;
+        if (e < TOTAL) v[i] = __ldg(grad_pixels + base + (size_t)(e / VEC) * pitch + (e % VEC));
+    }
+#pragma unroll
+    for (int i = 0; i < PER_LANE; ++i) {
+        const int e = i * 32 + lane;
+        if (e < TOTAL) grad_background[base + (size_t)(e / VEC) * pitch + (e % VEC)] = v[i];
+    }
+}
+
 // G-buffer entry of a face at a pixel, from the tile's face table
 __device__ __forceinline__ float4 table_gbuffer(const SlotRec* __restrict__ table, int slot, int col, int row)
 {
@@ -580,7 +612,12 @@ __global__ void __launch_bounds__(NW * 32, DIRT_BWD_MIN_BLOCKS * DIRT_BWD_WARPS 
     const unsigned later = flagmask & ~((2u << bi) - 1u);
     const int nb = later ? __ffs(later) - 1 : n_img;
 
-    // ---- grad_pixels of this lane's pixels: needed on every path, so the loads go out first
+    const bool flagged = (flagmask >> bi) & 1u;
+    // whole unflagged tiles were copied by background_copy_kernel (split launch): nothing at all to do here
+    const bool copied_already = !flagged && (flags & BWD_BACKGROUND_COPIED) && ((tx >> 1) + 1) * TILE_W <= W && (ty + 1) * TILE_H <= H;
+    if (copied_already) continue;
+
+    // ---- grad_pixels of this lane's pixels: needed on every other path, so the loads go out first
     float gp[2][C];
 #pragma unroll
     for (int pix = 0; pix < 2; ++pix) {
@@ -596,7 +633,6 @@ __global__ void __launch_bounds__(NW * 32, DIRT_BWD_MIN_BLOCKS * DIRT_BWD_WARPS 
             for (int ch = 0; ch < C; ++ch) gp[pix][ch] = __ldg(grad_pixels + p * cs + c0 + ch);
         }
     }
-    const bool flagged = (flagmask >> bi) & 1u;
 
     // ---- (1) stage the halo of face ids and pixels (unless they were requested while the previous image was processed)
     if (flagged) {
@@ -1064,6 +1100,21 @@ cudaError_t launch_backward(const float* vertices, const float* pixels, const fl
     const bool fused4 = d.C == 4 && groups.n == 2 && groups.width[0] == 3 && groups.width[1] == 1 &&
                         (((uintptr_t)pixels | (uintptr_t)grad_pixels | (uintptr_t)grad_background | (uintptr_t)grad_vertex_colors) % 16 == 0);
     const unsigned char* tflags = tile_flags_valid ? ws.tile_flags : nullptr;
+#if DIRT_BWD_SPLIT
+    // tiles no face can reach: a streaming kernel of their own (grad_background = grad_pixels, every channel at once)
+    if (tflags && !(flags & BWD_SKIP_COLOUR) && (d.W * d.C) % 4 == 0 && (TILE_W * d.C) % 4 == 0 &&
+        (((uintptr_t)grad_pixels | (uintptr_t)grad_background) % 16 == 0) && (d.C == 4 || d.C == 3 || d.C == 1) &&
+        (fused4 || groups.n == 1)) {
+        const dim3 cgrid((unsigned)((d.tiles_x + 3) / 4), (unsigned)d.tiles_y, (unsigned)d.B);
+        const float4* src = reinterpret_cast<const float4*>(grad_pixels);
+        float4* dst = reinterpret_cast<float4*>(grad_background);
+        if (d.C == 4) background_copy_kernel<16><<<cgrid, 128, 0, stream>>>(src, dst, tflags, d);
+        else if (d.C == 3) background_copy_kernel<12><<<cgrid, 128, 0, stream>>>(src, dst, tflags, d);
+        else background_copy_kernel<4><<<cgrid, 128, 0, stream>>>(src, dst, tflags, d);
+        ++*launches;
+        flags |= BWD_BACKGROUND_COPIED;
+    }
+#endif
     // TMA staging needs tensors it can describe: the group is the whole pixel (cs == C), rows are multiples of 16 bytes
     // and the bases 16-byte aligned; everything else is staged with per-lane cp.async
     CUtensorMap px_map, ids_map;

@@ -347,6 +347,7 @@ cudaError_t launch_backward(const float* vertices, const float* pixels, const fl
                             bool tile_flags_valid, int flags, unsigned long long expect_tag, cudaStream_t stream,
                             int* launches);   // flags: DIRT_BWD_* of include/dirt_b200.h; expect_tag != 0: the records are
                                               // promised to carry this tag (checked on the device)
-constexpr int BWD_SHARED_GEOMETRY = 1, BWD_SKIP_POSITION = 2, BWD_SKIP_COLOUR = 4;   // == DIRT_BWD_* (static_assert in api.cu)
+constexpr int BWD_SHARED_GEOMETRY = 1, BWD_SKIP_POSITION = 2, BWD_SKIP_COLOUR = 4;
+constexpr int BWD_BACKGROUND_COPIED = 1 << 16;   // internal: whole unflagged tiles were copied by background_copy_kernel   // == DIRT_BWD_* (static_assert in api.cu)
 
 }  // namespace dirt
