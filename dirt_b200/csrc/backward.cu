@@ -60,6 +60,9 @@ namespace dirt {
 #ifndef DIRT_BWD_TMA
 #define DIRT_BWD_TMA 1
 #endif
+#ifndef DIRT_BWD_SCHARR_EARLY
+#define DIRT_BWD_SCHARR_EARLY 0   // 1: the Scharr sums are formed while the face-table copies are in flight
+#endif
 #ifndef DIRT_BWD_SPLIT
 #define DIRT_BWD_SPLIT 0        // 1: tiles no face can reach are copied (grad_background = grad_pixels) by a streaming kernel of
 #endif                          // their own; the tile kernel then only checks their flag
@@ -759,9 +762,54 @@ __global__ void __launch_bounds__(NW * 32, DIRT_BWD_MIN_BLOCKS * DIRT_BWD_WARPS 
         cp_async_commit();
     }
 
+#if DIRT_BWD_SCHARR_EARLY
+    // Scharr sums while the face-table copies are in flight (they need the pixel halo only)
+    float e_dLdx[2] = {0.f, 0.f}, e_dLdy[2] = {0.f, 0.f}, e_gx1[2] = {0.f, 0.f}, e_gy1[2] = {0.f, 0.f};
+    int e_step0[2] = {0, 0}, e_step1[2] = {0, 0};
+    if (use_tma && want_pos) { mbar_wait(&bars[1], parity_px); parity_px ^= 1; }
+    if (want_pos) {
+        const bool staged_taps = (tcol0 + TILE - 1 + REACH) <= W - 1;
+#pragma unroll
+        for (int pix = 0; pix < 2; ++pix) {
+            if (!(pix ? near1 : near0)) continue;
+            const int row = row0 + pix;
+            const bool interior = pix ? interior1 : interior0;
+            // Scharr sums -> gradient scalars and dilation steps of the group(s)
+            float sx[3], sy[3], sx1[3], sy1[3];
+            if (staged_taps) {
+                if (C == 4) scharr_smem_c4(tile, lrow0 + pix + 1, lcol + 1, sx, sy, sx1, sy1);
+                else scharr_smem<C, N0>(tile, lrow0 + pix + 1, lcol + 1 + PxTile<C>::COL0, sx, sy);
+            } else {
+                float t[6];
+                scharr_global_call<N0>(pixels, b, row, col, d.B, H, W, cs, c0, t);
+#pragma unroll
+                for (int k = 0; k < 3; ++k) { sx[k] = t[k]; sy[k] = t[3 + k]; }
+                if (TWO_GROUPS) {
+                    scharr_global_call<1>(pixels, b, row, col, d.B, H, W, cs, c0 + 3, t);
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) { sx1[k] = t[k]; sy1[k] = t[3 + k]; }
+                }
+            }
+            float dLdx = 0.f, dLdy = 0.f, gx1 = 0.f, gy1 = 0.f;
+#pragma unroll
+            for (int ch = 0; ch < N0; ++ch) { dLdx += gp[pix][ch] * sx[ch]; dLdy += gp[pix][ch] * sy[ch]; }
+            const int step0 = interior ? dilation_step(sx, sy, col, row) : 0;
+            int step1 = 0;
+            if (TWO_GROUPS) {
+                gx1 = gp[pix][3 % C] * sx1[0]; gy1 = gp[pix][3 % C] * sy1[0];
+                step1 = interior ? dilation_step(sx1, sy1, col, row) : 0;
+            }
+
+            e_dLdx[pix] = dLdx; e_dLdy[pix] = dLdy; e_gx1[pix] = gx1; e_gy1[pix] = gy1; e_step0[pix] = step0; e_step1[pix] = step1;
+        }
+    }
+#endif
+
     // ---- (3) G-buffer tile: this lane's two pixels and its ring cell ---------------------------------------------------
     cp_async_wait_all();
+#if !DIRT_BWD_SCHARR_EARLY
     if (use_tma && want_pos) { mbar_wait(&bars[1], parity_px); parity_px ^= 1; }
+#endif
     __syncwarp();   // table and pixel halo complete; every lane has read its face ids (the G-buffer tile reuses their bytes)
     const float inf = __int_as_float(0x7f800000);
     float4 own[2];
@@ -807,6 +855,10 @@ __global__ void __launch_bounds__(NW * 32, DIRT_BWD_MIN_BLOCKS * DIRT_BWD_WARPS 
         sc[pix][C] = gp[pix][0]; sc[pix][C + 1] = gp[pix][0]; sc[pix][C + 2] = gp[pix][0];
         continue;
 #endif
+#if DIRT_BWD_SCHARR_EARLY
+        const float dLdx = e_dLdx[pix], dLdy = e_dLdy[pix], gx1 = e_gx1[pix], gy1 = e_gy1[pix];
+        const int step0 = e_step0[pix], step1 = e_step1[pix];
+#else
         // Scharr sums -> gradient scalars and dilation steps of the group(s)
         float sx[3], sy[3], sx1[3], sy1[3];
         if (staged_taps) {
@@ -832,6 +884,8 @@ __global__ void __launch_bounds__(NW * 32, DIRT_BWD_MIN_BLOCKS * DIRT_BWD_WARPS 
             gx1 = gp[pix][3 % C] * sx1[0]; gy1 = gp[pix][3 % C] * sy1[0];
             step1 = interior ? dilation_step(sx1, sy1, col, row) : 0;
         }
+
+#endif
 
         // dilation (:155-194): the neighbour at +step, else the one at -step, replaces this pixel's fragment if it is
         // covered, is a different triangle (vertex triple) and is nearer.  Returns the G-buffer cell the fragment comes from.
