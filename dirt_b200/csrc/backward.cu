@@ -1155,19 +1155,27 @@ cudaError_t launch_backward(const float* vertices, const float* pixels, const fl
                         (((uintptr_t)pixels | (uintptr_t)grad_pixels | (uintptr_t)grad_background | (uintptr_t)grad_vertex_colors) % 16 == 0);
     const unsigned char* tflags = tile_flags_valid ? ws.tile_flags : nullptr;
 #if DIRT_BWD_SPLIT
-    // tiles no face can reach: a streaming kernel of their own (grad_background = grad_pixels, every channel at once)
+    // tiles no face can reach: a streaming kernel of their own (grad_background = grad_pixels, every channel at once) on a
+    // second stream, under the tile kernel (which then only checks their flag)
+    bool forked = false;
     if (tflags && !(flags & BWD_SKIP_COLOUR) && (d.W * d.C) % 4 == 0 && (TILE_W * d.C) % 4 == 0 &&
         (((uintptr_t)grad_pixels | (uintptr_t)grad_background) % 16 == 0) && (d.C == 4 || d.C == 3 || d.C == 1) &&
-        (fused4 || groups.n == 1)) {
+        (fused4 || groups.n == 1) && side_stream().ok()) {
+        SideStream& ss = side_stream();
+        if ((e = ss.fork(stream)) != cudaSuccess) return e;
         const dim3 cgrid((unsigned)((d.tiles_x + 3) / 4), (unsigned)d.tiles_y, (unsigned)d.B);
         const float4* src = reinterpret_cast<const float4*>(grad_pixels);
         float4* dst = reinterpret_cast<float4*>(grad_background);
-        if (d.C == 4) background_copy_kernel<16><<<cgrid, 128, 0, stream>>>(src, dst, tflags, d);
-        else if (d.C == 3) background_copy_kernel<12><<<cgrid, 128, 0, stream>>>(src, dst, tflags, d);
-        else background_copy_kernel<4><<<cgrid, 128, 0, stream>>>(src, dst, tflags, d);
+        if (d.C == 4) background_copy_kernel<16><<<cgrid, 128, 0, ss.side>>>(src, dst, tflags, d);
+        else if (d.C == 3) background_copy_kernel<12><<<cgrid, 128, 0, ss.side>>>(src, dst, tflags, d);
+        else background_copy_kernel<4><<<cgrid, 128, 0, ss.side>>>(src, dst, tflags, d);
         ++*launches;
         flags |= BWD_BACKGROUND_COPIED;
+        forked = true;
     }
+    const auto join = [&]() -> cudaError_t { return forked ? side_stream().join(stream) : cudaSuccess; };
+#else
+    const auto join = [&]() -> cudaError_t { return cudaSuccess; };
 #endif
     // TMA staging needs tensors it can describe: the group is the whole pixel (cs == C), rows are multiples of 16 bytes
     // and the bases 16-byte aligned; everything else is staged with per-lane cp.async
@@ -1187,7 +1195,8 @@ cudaError_t launch_backward(const float* vertices, const float* pixels, const fl
                                                 grad_vertices, grad_vertex_colors, ws, d, tflags, d.C, c0, gstride, flags, expect_tag, stream))
     if (fused4) {
         ++*launches;
-        const cudaError_t le = DIRT_LAUNCH(4, DIRT_BWD_SLOTS_C4, 0);
+        cudaError_t le = DIRT_LAUNCH(4, DIRT_BWD_SLOTS_C4, 0);
+        if (le == cudaSuccess) le = join();
         return le != cudaSuccess ? le : finish();
     }
     int c0 = 0;
@@ -1198,6 +1207,7 @@ cudaError_t launch_backward(const float* vertices, const float* pixels, const fl
         if (le != cudaSuccess) return le;
     }
 #undef DIRT_LAUNCH
+    if ((e = join()) != cudaSuccess) return e;
     return finish();
 }
 

@@ -305,6 +305,19 @@ struct GroupSpec {
     unsigned char width[MAX_GROUPS];
 };
 
+// ---- a second stream for work that overlaps the call's main kernel (thread-local, created on first use) -------------
+// fork(): everything enqueued on `side` afterwards starts after what the caller's stream holds now;
+// join(): the caller's stream waits for it.  Both are event record/wait pairs, so a CUDA-graph capture of the caller's
+// stream follows onto the side stream and back.
+struct SideStream {
+    cudaStream_t side = nullptr;
+    cudaEvent_t forked = nullptr, joined = nullptr;
+    bool ok();
+    cudaError_t fork(cudaStream_t main);
+    cudaError_t join(cudaStream_t main);
+};
+SideStream& side_stream();   // thread-local, defined in api.cu
+
 // ---- optional per-kernel timing (dirt_kernel_timer_enable) -------------------------------------
 struct KernelTimer {
     int which = 0;  // 0 off, 1 forward raster kernel, 2 backward kernel
