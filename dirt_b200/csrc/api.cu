@@ -37,33 +37,6 @@ KernelTimer& kernel_timer()
     static thread_local KernelTimer t;
     return t;
 }
-SideStream& side_stream()
-{
-    static thread_local SideStream s;
-    return s;
-}
-bool SideStream::ok()
-{
-    if (side) return true;
-    if (cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking) != cudaSuccess) { side = nullptr; return false; }
-    if (cudaEventCreateWithFlags(&forked, cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&joined, cudaEventDisableTiming) != cudaSuccess) {
-        cudaStreamDestroy(side);
-        side = nullptr;
-        return false;
-    }
-    return true;
-}
-cudaError_t SideStream::fork(cudaStream_t main)
-{
-    cudaError_t e = cudaEventRecord(forked, main);
-    return e != cudaSuccess ? e : cudaStreamWaitEvent(side, forked, 0);
-}
-cudaError_t SideStream::join(cudaStream_t main)
-{
-    cudaError_t e = cudaEventRecord(joined, side);
-    return e != cudaSuccess ? e : cudaStreamWaitEvent(main, joined, 0);
-}
 }  // namespace dirt
 
 extern "C" int dirt_kernel_timer_enable(int which)

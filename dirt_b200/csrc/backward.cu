@@ -60,12 +60,6 @@ namespace dirt {
 #ifndef DIRT_BWD_TMA
 #define DIRT_BWD_TMA 1
 #endif
-#ifndef DIRT_BWD_SCHARR_EARLY
-#define DIRT_BWD_SCHARR_EARLY 0   // 1: the Scharr sums are formed while the face-table copies are in flight
-#endif
-#ifndef DIRT_BWD_SPLIT
-#define DIRT_BWD_SPLIT 0        // 1: tiles no face can reach are copied (grad_background = grad_pixels) by a streaming kernel of
-#endif                          // their own; the tile kernel then only checks their flag
 #ifndef DIRT_BWD_IMAGES
 #define DIRT_BWD_IMAGES 1       // consecutive images a warp walks at its tile position, the next image's halos requested (TMA)
 #endif                          // while the current one is processed.  Measured at cfg3: 1 -> 363 us, 2 / 4 / 8 -> 410 / 408 / 415 us
@@ -327,8 +321,8 @@ struct TransposedReduce<N, 0> {
 };
 
 // Which finished sum a lane owns after the butterfly, as a destination: bits 0-1 = vertex k of the face, bits 2-3 =
-// component inside the vertex's row, bit 4 = row of grad_vertices (else grad_vertex_colors); -1 = none.  A table in
-// constant memory because the compiler, short of registers, otherwise recomputes the index arithmetic (~40 instructions)
+// component inside the vertex's row, bit 4 = row of grad_vertices (else grad_vertex_colors); -1 = none.  A table
+// because the compiler, short of registers, otherwise recomputes the index arithmetic (~40 instructions)
 // for every face of every tile.
 template <int C>
 struct OwnerTable {
@@ -359,13 +353,14 @@ constexpr OwnerTable<C> make_owner_table()
     }
     return t;
 }
-__constant__ OwnerTable<1> c_owner1 = make_owner_table<1>();
-__constant__ OwnerTable<3> c_owner3 = make_owner_table<3>();
-__constant__ OwnerTable<4> c_owner4 = make_owner_table<4>();
+// global (not __constant__) memory: every lane reads its own entry, which the constant cache would serialise 32-fold
+__device__ const OwnerTable<1> g_owner1 = make_owner_table<1>();
+__device__ const OwnerTable<3> g_owner3 = make_owner_table<3>();
+__device__ const OwnerTable<4> g_owner4 = make_owner_table<4>();
 template <int C>
 __device__ __forceinline__ int owner_meta(int lane)
 {
-    return C == 1 ? c_owner1.meta[lane] : C == 3 ? c_owner3.meta[lane] : c_owner4.meta[lane];
+    return __ldg(C == 1 ? &g_owner1.meta[lane] : C == 3 ? &g_owner3.meta[lane] : &g_owner4.meta[lane]);
 }
 
 // ---- reference-shaped path for one tile (face table overflow): one atomic per term ---------------------------------
@@ -455,35 +450,6 @@ __device__ __noinline__ void tile_generic(const float* __restrict__ vertices, co
                 }
             }
         }
-    }
-}
-
-// grad_background = grad_pixels on whole 16x8 tiles that the forward pass left unflagged (no face on them or next to
-// them), all channels at once: one warp per tile, every lane's copies in flight together.  VEC = float4 per tile row.
-template <int VEC>
-__global__ void __launch_bounds__(128) background_copy_kernel(const float4* __restrict__ grad_pixels, float4* __restrict__ grad_background,
-                                                              const unsigned char* __restrict__ tile_flags, Dims d)
-{
-    const int lane = threadIdx.x & 31;
-    const int tx = blockIdx.x * 4 + (int)__reduce_min_sync(0xffffffffu, threadIdx.x >> 5), ty = blockIdx.y, b = blockIdx.z;
-    if (tx >= d.tiles_x) return;
-    if ((tx + 1) * TILE_W > d.W || (ty + 1) * TILE_H > d.H) return;   // partial tiles stay with the tile kernel
-    if (tile_flags[(size_t)b * d.tiles + ty * d.tiles_x + tx] != 0) return;
-    // a tile row is TILE_W pixels = VEC float4 (VEC = 4 * C for... see the launcher); row pitch in float4 = W * C / 4
-    const size_t pitch = (size_t)d.W * VEC / TILE_W;
-    const size_t base = ((size_t)b * d.H + (size_t)ty * TILE_H) * pitch + (size_t)tx * VEC;
-    constexpr int TOTAL = VEC * TILE_H;            // float4 per tile
-    constexpr int PER_LANE = (TOTAL + 31) / 32;
-    float4 v[PER_LANE];
-#pragma unroll
-    for (int i = 0; i < PER_LANE; ++i) {
-        const int e = i * 32 + lane;
-        if (e < TOTAL) v[i] = __ldg(grad_pixels + base + (size_t)(e / VEC) * pitch + (e % VEC));
-    }
-#pragma unroll
-    for (int i = 0; i < PER_LANE; ++i) {
-        const int e = i * 32 + lane;
-        if (e < TOTAL) grad_background[base + (size_t)(e / VEC) * pitch + (e % VEC)] = v[i];
     }
 }
 
@@ -616,10 +582,6 @@ __global__ void __launch_bounds__(NW * 32, DIRT_BWD_MIN_BLOCKS * DIRT_BWD_WARPS 
     const int nb = later ? __ffs(later) - 1 : n_img;
 
     const bool flagged = (flagmask >> bi) & 1u;
-    // whole unflagged tiles were copied by background_copy_kernel (split launch): nothing at all to do here
-    const bool copied_already = !flagged && (flags & BWD_BACKGROUND_COPIED) && ((tx >> 1) + 1) * TILE_W <= W && (ty + 1) * TILE_H <= H;
-    if (copied_already) continue;
-
     // ---- grad_pixels of this lane's pixels: needed on every other path, so the loads go out first
     float gp[2][C];
 #pragma unroll
@@ -762,54 +724,9 @@ __global__ void __launch_bounds__(NW * 32, DIRT_BWD_MIN_BLOCKS * DIRT_BWD_WARPS 
         cp_async_commit();
     }
 
-#if DIRT_BWD_SCHARR_EARLY
-    // Scharr sums while the face-table copies are in flight (they need the pixel halo only)
-    float e_dLdx[2] = {0.f, 0.f}, e_dLdy[2] = {0.f, 0.f}, e_gx1[2] = {0.f, 0.f}, e_gy1[2] = {0.f, 0.f};
-    int e_step0[2] = {0, 0}, e_step1[2] = {0, 0};
-    if (use_tma && want_pos) { mbar_wait(&bars[1], parity_px); parity_px ^= 1; }
-    if (want_pos) {
-        const bool staged_taps = (tcol0 + TILE - 1 + REACH) <= W - 1;
-#pragma unroll
-        for (int pix = 0; pix < 2; ++pix) {
-            if (!(pix ? near1 : near0)) continue;
-            const int row = row0 + pix;
-            const bool interior = pix ? interior1 : interior0;
-            // Scharr sums -> gradient scalars and dilation steps of the group(s)
-            float sx[3], sy[3], sx1[3], sy1[3];
-            if (staged_taps) {
-                if (C == 4) scharr_smem_c4(tile, lrow0 + pix + 1, lcol + 1, sx, sy, sx1, sy1);
-                else scharr_smem<C, N0>(tile, lrow0 + pix + 1, lcol + 1 + PxTile<C>::COL0, sx, sy);
-            } else {
-                float t[6];
-                scharr_global_call<N0>(pixels, b, row, col, d.B, H, W, cs, c0, t);
-#pragma unroll
-                for (int k = 0; k < 3; ++k) { sx[k] = t[k]; sy[k] = t[3 + k]; }
-                if (TWO_GROUPS) {
-                    scharr_global_call<1>(pixels, b, row, col, d.B, H, W, cs, c0 + 3, t);
-#pragma unroll
-                    for (int k = 0; k < 3; ++k) { sx1[k] = t[k]; sy1[k] = t[3 + k]; }
-                }
-            }
-            float dLdx = 0.f, dLdy = 0.f, gx1 = 0.f, gy1 = 0.f;
-#pragma unroll
-            for (int ch = 0; ch < N0; ++ch) { dLdx += gp[pix][ch] * sx[ch]; dLdy += gp[pix][ch] * sy[ch]; }
-            const int step0 = interior ? dilation_step(sx, sy, col, row) : 0;
-            int step1 = 0;
-            if (TWO_GROUPS) {
-                gx1 = gp[pix][3 % C] * sx1[0]; gy1 = gp[pix][3 % C] * sy1[0];
-                step1 = interior ? dilation_step(sx1, sy1, col, row) : 0;
-            }
-
-            e_dLdx[pix] = dLdx; e_dLdy[pix] = dLdy; e_gx1[pix] = gx1; e_gy1[pix] = gy1; e_step0[pix] = step0; e_step1[pix] = step1;
-        }
-    }
-#endif
-
     // ---- (3) G-buffer tile: this lane's two pixels and its ring cell ---------------------------------------------------
     cp_async_wait_all();
-#if !DIRT_BWD_SCHARR_EARLY
     if (use_tma && want_pos) { mbar_wait(&bars[1], parity_px); parity_px ^= 1; }
-#endif
     __syncwarp();   // table and pixel halo complete; every lane has read its face ids (the G-buffer tile reuses their bytes)
     const float inf = __int_as_float(0x7f800000);
     float4 own[2];
@@ -855,10 +772,6 @@ __global__ void __launch_bounds__(NW * 32, DIRT_BWD_MIN_BLOCKS * DIRT_BWD_WARPS 
         sc[pix][C] = gp[pix][0]; sc[pix][C + 1] = gp[pix][0]; sc[pix][C + 2] = gp[pix][0];
         continue;
 #endif
-#if DIRT_BWD_SCHARR_EARLY
-        const float dLdx = e_dLdx[pix], dLdy = e_dLdy[pix], gx1 = e_gx1[pix], gy1 = e_gy1[pix];
-        const int step0 = e_step0[pix], step1 = e_step1[pix];
-#else
         // Scharr sums -> gradient scalars and dilation steps of the group(s)
         float sx[3], sy[3], sx1[3], sy1[3];
         if (staged_taps) {
@@ -884,8 +797,6 @@ __global__ void __launch_bounds__(NW * 32, DIRT_BWD_MIN_BLOCKS * DIRT_BWD_WARPS 
             gx1 = gp[pix][3 % C] * sx1[0]; gy1 = gp[pix][3 % C] * sy1[0];
             step1 = interior ? dilation_step(sx1, sy1, col, row) : 0;
         }
-
-#endif
 
         // dilation (:155-194): the neighbour at +step, else the one at -step, replaces this pixel's fragment if it is
         // covered, is a different triangle (vertex triple) and is nearer.  Returns the G-buffer cell the fragment comes from.
@@ -1154,29 +1065,6 @@ cudaError_t launch_backward(const float* vertices, const float* pixels, const fl
     const bool fused4 = d.C == 4 && groups.n == 2 && groups.width[0] == 3 && groups.width[1] == 1 &&
                         (((uintptr_t)pixels | (uintptr_t)grad_pixels | (uintptr_t)grad_background | (uintptr_t)grad_vertex_colors) % 16 == 0);
     const unsigned char* tflags = tile_flags_valid ? ws.tile_flags : nullptr;
-#if DIRT_BWD_SPLIT
-    // tiles no face can reach: a streaming kernel of their own (grad_background = grad_pixels, every channel at once) on a
-    // second stream, under the tile kernel (which then only checks their flag)
-    bool forked = false;
-    if (tflags && !(flags & BWD_SKIP_COLOUR) && (d.W * d.C) % 4 == 0 && (TILE_W * d.C) % 4 == 0 &&
-        (((uintptr_t)grad_pixels | (uintptr_t)grad_background) % 16 == 0) && (d.C == 4 || d.C == 3 || d.C == 1) &&
-        (fused4 || groups.n == 1) && side_stream().ok()) {
-        SideStream& ss = side_stream();
-        if ((e = ss.fork(stream)) != cudaSuccess) return e;
-        const dim3 cgrid((unsigned)((d.tiles_x + 3) / 4), (unsigned)d.tiles_y, (unsigned)d.B);
-        const float4* src = reinterpret_cast<const float4*>(grad_pixels);
-        float4* dst = reinterpret_cast<float4*>(grad_background);
-        if (d.C == 4) background_copy_kernel<16><<<cgrid, 128, 0, ss.side>>>(src, dst, tflags, d);
-        else if (d.C == 3) background_copy_kernel<12><<<cgrid, 128, 0, ss.side>>>(src, dst, tflags, d);
-        else background_copy_kernel<4><<<cgrid, 128, 0, ss.side>>>(src, dst, tflags, d);
-        ++*launches;
-        flags |= BWD_BACKGROUND_COPIED;
-        forked = true;
-    }
-    const auto join = [&]() -> cudaError_t { return forked ? side_stream().join(stream) : cudaSuccess; };
-#else
-    const auto join = [&]() -> cudaError_t { return cudaSuccess; };
-#endif
     // TMA staging needs tensors it can describe: the group is the whole pixel (cs == C), rows are multiples of 16 bytes
     // and the bases 16-byte aligned; everything else is staged with per-lane cp.async
     CUtensorMap px_map, ids_map;
@@ -1195,8 +1083,7 @@ cudaError_t launch_backward(const float* vertices, const float* pixels, const fl
                                                 grad_vertices, grad_vertex_colors, ws, d, tflags, d.C, c0, gstride, flags, expect_tag, stream))
     if (fused4) {
         ++*launches;
-        cudaError_t le = DIRT_LAUNCH(4, DIRT_BWD_SLOTS_C4, 0);
-        if (le == cudaSuccess) le = join();
+        const cudaError_t le = DIRT_LAUNCH(4, DIRT_BWD_SLOTS_C4, 0);
         return le != cudaSuccess ? le : finish();
     }
     int c0 = 0;
@@ -1207,7 +1094,6 @@ cudaError_t launch_backward(const float* vertices, const float* pixels, const fl
         if (le != cudaSuccess) return le;
     }
 #undef DIRT_LAUNCH
-    if ((e = join()) != cudaSuccess) return e;
     return finish();
 }
 

@@ -305,19 +305,6 @@ struct GroupSpec {
     unsigned char width[MAX_GROUPS];
 };
 
-// ---- a second stream for work that overlaps the call's main kernel (thread-local, created on first use) -------------
-// fork(): everything enqueued on `side` afterwards starts after what the caller's stream holds now;
-// join(): the caller's stream waits for it.  Both are event record/wait pairs, so a CUDA-graph capture of the caller's
-// stream follows onto the side stream and back.
-struct SideStream {
-    cudaStream_t side = nullptr;
-    cudaEvent_t forked = nullptr, joined = nullptr;
-    bool ok();
-    cudaError_t fork(cudaStream_t main);
-    cudaError_t join(cudaStream_t main);
-};
-SideStream& side_stream();   // thread-local, defined in api.cu
-
 // ---- optional per-kernel timing (dirt_kernel_timer_enable) -------------------------------------
 struct KernelTimer {
     int which = 0;  // 0 off, 1 forward raster kernel, 2 backward kernel
@@ -360,7 +347,6 @@ cudaError_t launch_backward(const float* vertices, const float* pixels, const fl
                             bool tile_flags_valid, int flags, unsigned long long expect_tag, cudaStream_t stream,
                             int* launches);   // flags: DIRT_BWD_* of include/dirt_b200.h; expect_tag != 0: the records are
                                               // promised to carry this tag (checked on the device)
-constexpr int BWD_SHARED_GEOMETRY = 1, BWD_SKIP_POSITION = 2, BWD_SKIP_COLOUR = 4;
-constexpr int BWD_BACKGROUND_COPIED = 1 << 16;   // internal: whole unflagged tiles were copied by background_copy_kernel   // == DIRT_BWD_* (static_assert in api.cu)
+constexpr int BWD_SHARED_GEOMETRY = 1, BWD_SKIP_POSITION = 2, BWD_SKIP_COLOUR = 4;   // == DIRT_BWD_* (static_assert in api.cu)
 
 }  // namespace dirt

@@ -32,9 +32,6 @@ constexpr int WARPS_PER_BLOCK = DIRT_RASTER_WARPS;
 #define DIRT_RASTER_TILES 2   // tiles (neighbours in x) per warp: measured 0.167 -> 0.152 ms at cfg3 (empty pairs are copied together)
 #endif
 constexpr int TILES_PER_WARP = DIRT_RASTER_TILES;
-#ifndef DIRT_FWD_SPLIT
-#define DIRT_FWD_SPLIT 0   // 1: whole tiles with nothing binned to them are copied by a streaming kernel on a second stream
-#endif
 #ifndef DIRT_RASTER_PREFETCH_BG
 #define DIRT_RASTER_PREFETCH_BG 0
 #endif
@@ -291,8 +288,8 @@ template <int MODE, int CT, bool REC>
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, DIRT_RASTER_MIN_BLOCKS) raster_kernel(
     const float* __restrict__ vertices, const float* __restrict__ background,
     const float* __restrict__ vertex_colors, float* __restrict__ pixels, int32_t* __restrict__ face_ids_out,
-    float* __restrict__ gbuffer_out, Workspace ws, Dims d, int empty_copied)   // empty_copied: whole empty tiles were
-{                                                                               // written by empty_tile_copy_kernel
+    float* __restrict__ gbuffer_out, Workspace ws, Dims d)
+{
     __shared__ Slot slots_all[WARPS_PER_BLOCK][32];
     // grid: x = groups of WARPS_PER_BLOCK * TILES_PER_WARP tiles along a tile row, y = tile row, z = image
     const int lane = threadIdx.x & 31;
@@ -313,7 +310,6 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, DIRT_RASTER_MIN_BLOCKS) 
         const int* cp = ws.tile_count + (size_t)b * d.tiles + ty * d.tiles_x + txb;
         const int cnt_a = cp[0], cnt_b = cp[1];
         if (cnt_a == 0 && cnt_b == 0 && ws.large_count[b] == 0) {
-            if (empty_copied) continue;
             const int col0 = txb * TILE_W + (lane & 7) * 2, row0 = trow0 + (lane >> 3) * 2;
             const size_t p00 = ((size_t)b * d.H + row0) * d.W + col0;
             if (CT == 4) {
@@ -372,7 +368,6 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, DIRT_RASTER_MIN_BLOCKS) 
 
     // ---- nothing binned to this tile: the background passes through ----------------------------------------
     if (nbin == 0 && nlarge == 0) {
-        if (empty_copied && whole) continue;
         if (MODE == 0 && CT == 3 && whole) {
             const float2* src = reinterpret_cast<const float2*>(background);
             float2* dst = reinterpret_cast<float2*>(pixels);
@@ -467,38 +462,6 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, DIRT_RASTER_MIN_BLOCKS) 
     }   // b
 }
 
-// pixels = background (and face ids = -1) on whole 16x8 tiles that nothing is binned to, every channel at once: one warp per
-// tile, all of a lane's copies in flight together (split launch, DIRT_FWD_SPLIT).  VEC = float4 per tile row.
-template <int VEC>
-__global__ void __launch_bounds__(128) empty_tile_copy_kernel(const float4* __restrict__ background, float4* __restrict__ pixels,
-                                                              int32_t* __restrict__ face_ids_out, Workspace ws, Dims d)
-{
-    const int lane = threadIdx.x & 31;
-    const int tx = blockIdx.x * 4 + (int)__reduce_min_sync(0xffffffffu, threadIdx.x >> 5), ty = blockIdx.y, b = blockIdx.z;
-    if (tx >= d.tiles_x) return;
-    if ((tx + 1) * TILE_W > d.W || (ty + 1) * TILE_H > d.H) return;   // partial tiles stay with the raster kernel
-    if (ws.tile_count[(size_t)b * d.tiles + ty * d.tiles_x + tx] != 0 || ws.large_count[b] != 0) return;
-    const size_t pitch = (size_t)d.W * VEC / TILE_W;
-    const size_t base = ((size_t)b * d.H + (size_t)ty * TILE_H) * pitch + (size_t)tx * VEC;
-    constexpr int TOTAL = VEC * TILE_H;
-    constexpr int PER_LANE = (TOTAL + 31) / 32;
-    float4 v[PER_LANE];
-#pragma unroll
-    for (int i = 0; i < PER_LANE; ++i) {
-        const int e = i * 32 + lane;
-        if (e < TOTAL) v[i] = __ldg(background + base + (size_t)(e / VEC) * pitch + (e % VEC));
-    }
-#pragma unroll
-    for (int i = 0; i < PER_LANE; ++i) {
-        const int e = i * 32 + lane;
-        if (e < TOTAL) pixels[base + (size_t)(e / VEC) * pitch + (e % VEC)] = v[i];
-    }
-    if (face_ids_out) {   // 16 x 8 ids = 32 int4
-        int4* ids = reinterpret_cast<int4*>(face_ids_out + ((size_t)b * d.H + (size_t)ty * TILE_H + (lane >> 2)) * d.W + tx * TILE_W) + (lane & 3);
-        *ids = make_int4(-1, -1, -1, -1);
-    }
-}
-
 cudaError_t launch_raster_forward(const float* vertices, const float* background, const float* vertex_colors, float* pixels,
                                   int32_t* face_ids_out, const Workspace& ws, const Dims& d, cudaStream_t stream,
                                   int* launches)
@@ -510,44 +473,21 @@ cudaError_t launch_raster_forward(const float* vertices, const float* background
                       ((uintptr_t)vertex_colors % 16 == 0);
     // C == 3 with an even width: every quad row (two pixels) is 24 contiguous, 8-byte aligned bytes
     const bool vec3 = d.C == 3 && d.W % 2 == 0 && ((uintptr_t)background % 8 == 0) && ((uintptr_t)pixels % 8 == 0);
-    int empty_copied = 0;
-#if DIRT_FWD_SPLIT
-    bool forked = false;
-    if ((d.C == 4 || d.C == 3 || d.C == 1) && (d.W * d.C) % 4 == 0 && d.W % 4 == 0 && (((uintptr_t)background | (uintptr_t)pixels | (uintptr_t)face_ids_out) % 16 == 0) &&
-        side_stream().ok()) {
-        SideStream& ss = side_stream();
-        cudaError_t fe = ss.fork(stream);
-        if (fe != cudaSuccess) return fe;
-        const dim3 cgrid((unsigned)((d.tiles_x + 3) / 4), (unsigned)d.tiles_y, (unsigned)d.B);
-        const float4* src = reinterpret_cast<const float4*>(background);
-        float4* dst = reinterpret_cast<float4*>(pixels);
-        if (d.C == 4) empty_tile_copy_kernel<16><<<cgrid, 128, 0, ss.side>>>(src, dst, face_ids_out, ws, d);
-        else if (d.C == 3) empty_tile_copy_kernel<12><<<cgrid, 128, 0, ss.side>>>(src, dst, face_ids_out, ws, d);
-        else empty_tile_copy_kernel<4><<<cgrid, 128, 0, ss.side>>>(src, dst, face_ids_out, ws, d);
-        ++*launches;
-        empty_copied = 1;
-        forked = true;
-    }
-#endif
     const bool rec = shade_records_ok(d);   // the setup pass of this call wrote the shading records (C <= 4)
     if (vec4 && rec)
         raster_kernel<0, 4, true><<<grid, WARPS_PER_BLOCK * 32, 0, stream>>>(vertices, background, vertex_colors, pixels,
-                                                                             face_ids_out, nullptr, ws, d, empty_copied);
+                                                                             face_ids_out, nullptr, ws, d);
     else if (vec3 && rec)
         raster_kernel<0, 3, true><<<grid, WARPS_PER_BLOCK * 32, 0, stream>>>(vertices, background, vertex_colors, pixels,
-                                                                             face_ids_out, nullptr, ws, d, empty_copied);
+                                                                             face_ids_out, nullptr, ws, d);
     else if (rec)
         raster_kernel<0, 0, true><<<grid, WARPS_PER_BLOCK * 32, 0, stream>>>(vertices, background, vertex_colors, pixels,
-                                                                             face_ids_out, nullptr, ws, d, empty_copied);
+                                                                             face_ids_out, nullptr, ws, d);
     else   // more than four channels (or a frame beyond the records' 16-bit reference pixel): barycentrics + colour gathers
         raster_kernel<0, 0, false><<<grid, WARPS_PER_BLOCK * 32, 0, stream>>>(vertices, background, vertex_colors, pixels,
-                                                                              face_ids_out, nullptr, ws, d, empty_copied);
+                                                                              face_ids_out, nullptr, ws, d);
     ++*launches;
-    cudaError_t le = cudaGetLastError();
-#if DIRT_FWD_SPLIT
-    if (le == cudaSuccess && forked) le = side_stream().join(stream);
-#endif
-    return le;
+    return cudaGetLastError();
 }
 
 cudaError_t launch_raster_visibility(const float* vertices, int32_t* face_ids, float* gbuffer, const Workspace& ws, const Dims& d,
@@ -555,7 +495,7 @@ cudaError_t launch_raster_visibility(const float* vertices, int32_t* face_ids, f
 {
     if ((long long)d.B * d.tiles == 0) return cudaSuccess;
     const dim3 grid((unsigned)((d.tiles_x + WARPS_PER_BLOCK * TILES_PER_WARP - 1) / (WARPS_PER_BLOCK * TILES_PER_WARP)), (unsigned)d.tiles_y, (unsigned)min(d.B, 65535));
-    raster_kernel<1, 0, false><<<grid, WARPS_PER_BLOCK * 32, 0, stream>>>(vertices, nullptr, nullptr, nullptr, face_ids, gbuffer, ws, d, 0);
+    raster_kernel<1, 0, false><<<grid, WARPS_PER_BLOCK * 32, 0, stream>>>(vertices, nullptr, nullptr, nullptr, face_ids, gbuffer, ws, d);
     ++*launches;
     return cudaGetLastError();
 }
