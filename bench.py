@@ -584,6 +584,10 @@ def run_ours(args):
             tr = json.load(f).get(args.workload, {}).get('backward' if dom == 'backward_kernel' else 'forward')
         if tr:
             traffic, traffic_src = tr['dram_bytes'], tr['source']
+            cap = tr.get('images')   # the capture ran a smaller batch than this launch: per-launch traffic scales with it
+            if cap and cap != B:
+                traffic = int(traffic * B / cap)
+                traffic_src += ' (captured at %d images per launch, scaled x%g to this launch of %d)' % (cap, B / cap, B)
     except Exception:
         pass
     roofline = {'bound': 'hbm', 'kernel': dom, 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
