@@ -213,8 +213,35 @@ class PreparedStep:
         self.launches_per_step = 0
         self.graphs = None
         self.parity = 0
-        self.comm_stream = torch.cuda.Stream(device)
+        self.comm_stream = torch.cuda.Stream(device, priority=-1)   # its few CTAs go ahead of the queued tiles
         self.comm_done = [None, None]
+        self.peer = None          # dirt_b200.distributed.PeerExchange when the ranks can map each other's memory
+        self.reduced_flat = None  # its output: the gradient summed over ranks, one buffer per step parity
+        self.collective = 'none (N=1)'
+
+    def setup_exchange(self, world, mode):
+        """The sum over ranks of shared_flat: the library's peer-memory kernel, or NCCL's all-reduce (in place) if the peer
+        mapping is unavailable / not wanted.  Collective: every rank calls it."""
+        torch = self.torch
+        V, C = self.dims[4], self.dims[3]
+        width = 4 + C
+        if world > 1 and mode != 'nccl':
+            try:
+                from dirt_b200.distributed import PeerExchange
+                self.peer = PeerExchange(V * width, self.device)
+                self.reduced_flat = [torch.zeros_like(f) for f in self.shared_flat]
+                self.collective = ('dirt_peer_exchange: [V,%d] fp32 gradient of the batch-shared geometry pushed into every peer\'s '
+                                   'memory and summed in rank order, one kernel of %d CTAs per rank and step on a side stream, '
+                                   'overlapping the next step' % (width, world))
+                return
+            except Exception as e:   # said out loud, and in the JSON line
+                if mode == 'peer':
+                    raise
+                sys.stderr.write('bench: peer exchange unavailable (%s: %s); using the NCCL all-reduce\n' % (type(e).__name__, e))
+                self.peer = None
+        if world > 1:
+            self.collective = ('nccl all_reduce([V,%d] fp32 gradient of the batch-shared geometry) once per step on a side stream, '
+                               'overlapping the next step' % width)
 
     def _p(self, t):
         return ctypes.c_void_p(t.data_ptr())
@@ -282,7 +309,10 @@ class PreparedStep:
             ready.record(cur)
             with torch.cuda.stream(self.comm_stream):
                 self.comm_stream.wait_event(ready)
-                dist.all_reduce(self.shared_flat[which], op=dist.ReduceOp.SUM)
+                if self.peer is not None:
+                    self.peer.exchange(self.shared_flat[which], self.reduced_flat[which], self.comm_stream)
+                else:
+                    dist.all_reduce(self.shared_flat[which], op=dist.ReduceOp.SUM)
                 done = torch.cuda.Event()
                 done.record(self.comm_stream)
             self.comm_done[which] = done
@@ -467,6 +497,7 @@ def run_ours(args):
     prep.local_step()
     if not args.no_graph:
         prep.capture()
+    prep.setup_exchange(world, args.collective)
     for _ in range(max(args.warmup, 3)):
         prep.step(world)
     prep.drain()
@@ -495,7 +526,37 @@ def run_ours(args):
         torch.cuda.synchronize(device)
     clocks = sampler.finish() if sampler else None
     t = torch.tensor([elapsed_ms], dtype=torch.float64, device=device)
+    multi = None
     if world > 1:
+        # what limits the N-GPU step: every rank's own time for the timed region, and the same K steps with the
+        # all-reduce left out (all ranks still running at once), each as the list over ranks
+        local_start, local_stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        sync_all()
+        local_start.record()
+        for _ in range(args.steps):
+            prep.step(1)
+        local_stop.record()
+        sync_all()
+        mine = torch.tensor([elapsed_ms / args.steps, local_start.elapsed_time(local_stop) / args.steps], dtype=torch.float64, device=device)
+        every = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(every, mine)
+        multi = {'per_rank_ms_per_step': [round(float(e[0]), 5) for e in every],
+                 'per_rank_ms_per_step_without_all_reduce': [round(float(e[1]), 5) for e in every]}
+        if prep.peer is not None:
+            # the peer-memory sum against NCCL's all-reduce of the same local buffers (outside the timed region)
+            prep.parity = 0
+            prep.step(world)
+            prep.drain()
+            torch.cuda.synchronize(device)
+            want = prep.shared_flat[0].clone()
+            dist.all_reduce(want, op=dist.ReduceOp.SUM)
+            got = prep.reduced_flat[0]
+            scale = float(want.abs().max().item()) + 1e-30
+            err = float((got - want).abs().max().item()) / scale
+            same = got.clone()
+            dist.broadcast(same, src=0)
+            multi['peer_exchange_check'] = {'max_err_over_max_abs_vs_nccl': err, 'ok': bool(err < 1e-5),
+                                            'bit_identical_to_rank0': bool(torch.equal(same, got))}
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     elapsed_ms = float(t.item())
     ms_per_step = elapsed_ms / args.steps
@@ -615,8 +676,7 @@ def run_ours(args):
         'data': 'synthetic',
         'config': {'workload': desc, 'name': args.workload, 'batch_per_gpu': B, 'global_batch': B * world, 'height': H, 'width': W,
                    'channels': C, 'vertices': V, 'faces': F, 'parallelism': 'batch-sharded x%d' % world,
-                   'collective': ('all_reduce([V,%d] fp32 gradient of the batch-shared geometry) once per step on a side stream, '
-                                  'overlapping the next step' % (4 + C)) if world > 1 else 'none (N=1)',
+                   'collective': prep.collective,
                    'vertex_gradients': 'accumulated over the batch in the backward kernel (DIRT_BWD_SHARED_GEOMETRY)',
                    'background': args.background,
                    'l2': 'inputs larger than L2 (%.0f MB touched per step)' % ((fwd_bytes + bwd_bytes) / 1e6)},
@@ -624,6 +684,8 @@ def run_ours(args):
         'gpu_launches': int(launches), 'gpu_launches_per_step': int(prep.launches_per_step), 'cuda_graph': prep.graphs is not None,
         'clocks': clocks, 'roofline': roofline, 'numa': numa,
     }
+    if multi:
+        out['multi_gpu'] = multi
     if checked is not None:
         out['checked'] = checked['ok']
         out['check'] = checked
@@ -729,6 +791,9 @@ def main():
     ap.add_argument('--cpu-sample', type=int, default=64, help='images the CPU baseline renders per pass')
     ap.add_argument('--background', default='zeros', choices=['zeros', 'uniform'], help='background values (BASELINE: zeros)')
     ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--collective', choices=['auto', 'peer', 'nccl'], default='auto',
+                    help='N>1: sum of the shared-geometry gradient over ranks by the library\'s peer-memory kernel (peer), by NCCL '
+                         '(nccl), or the first that is available (auto)')
     ap.add_argument('--no-graph', action='store_true', help='launch every step call by call instead of replaying a CUDA graph')
     ap.add_argument('--e2e-chunks', type=int, default=8, help='batch chunks of the host copy/compute pipeline')
     ap.add_argument('--no-cpu-baseline', action='store_true')

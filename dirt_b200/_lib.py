@@ -52,6 +52,10 @@ def lib():
     L.dirt_workspace_status.argtypes = [vp, sz] + [i] * 6 + [vp]
     L.dirt_rasterise_visibility.restype = i
     L.dirt_rasterise_visibility.argtypes = [vp] * 4 + [i] * 5 + [vp, sz, vp]
+    L.dirt_peer_exchange_bytes.restype = sz
+    L.dirt_peer_exchange_bytes.argtypes = [i, ctypes.c_longlong]
+    L.dirt_peer_exchange.restype = i
+    L.dirt_peer_exchange.argtypes = [vp, vp, ctypes.POINTER(vp), ctypes.POINTER(vp), i, i, ctypes.c_longlong, ctypes.c_uint, vp]
     L.dirt_kernel_timer_enable.restype = i
     L.dirt_kernel_timer_enable.argtypes = [i]
     L.dirt_kernel_timer_elapsed_ms.restype = ctypes.c_float
@@ -61,7 +65,7 @@ def lib():
 
 EXPORTED_SYMBOLS = ['dirt_error_string', 'dirt_abi_version', 'dirt_workspace_bytes', 'dirt_rasterise_forward',
                     'dirt_rasterise_backward', 'dirt_rasterise_backward_ex', 'dirt_workspace_status',
-                    'dirt_rasterise_visibility', 'dirt_last_launch_count',
+                    'dirt_rasterise_visibility', 'dirt_peer_exchange_bytes', 'dirt_peer_exchange', 'dirt_last_launch_count',
                     'dirt_kernel_timer_enable', 'dirt_kernel_timer_elapsed_ms']
 
 

@@ -8,7 +8,7 @@ import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 SO_PATH = os.path.join(_HERE, 'libdirt_b200.so')
-SOURCES = ['api.cu', 'setup.cu', 'raster.cu', 'backward.cu']
+SOURCES = ['api.cu', 'setup.cu', 'raster.cu', 'backward.cu', 'exchange.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
               '-Xcompiler', '-fPIC', '-shared']
 

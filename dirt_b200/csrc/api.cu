@@ -29,7 +29,7 @@ extern "C" const char* dirt_error_string(int code)
     }
 }
 
-extern "C" int dirt_abi_version(void) { return 3; }
+extern "C" int dirt_abi_version(void) { return 4; }
 
 namespace dirt {
 KernelTimer& kernel_timer()

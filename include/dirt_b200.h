@@ -131,6 +131,22 @@ int dirt_rasterise_visibility(const float* vertices, const int32_t* faces,
                               int B, int H, int W, int V, int F,
                               void* workspace, size_t workspace_bytes, void* cuda_stream);
 
+/* Multi-GPU (one process per GPU, one node): sum over the ranks of the batch-shared vertex gradient -- the [V,4 | V,C] buffer
+ * a DIRT_BWD_SHARED_GEOMETRY call fills -- over peer memory, as ONE kernel of `world` CTAs per rank and step: every rank
+ * pushes its buffer into its slot of every peer's exchange area (stores through the NVLink peer mapping), releases a flag
+ * there, waits for the `world` flags of its own area and adds its slots in rank order into `out` (bit-identical on all
+ * ranks).  The reference has no counterpart (no multi-GPU path: tests/multi_gpu_test.py); TensorFlow users would all-reduce
+ * the op's gradient outside it.
+ *   dirt_peer_exchange_bytes  size of one rank's exchange area for buffers of `count` floats (two step parities x world slots).
+ *   peer_slots[p] / peer_flags[p]  HOST arrays of `world` DEVICE pointers: rank p's exchange area / its flag words
+ *                                  (2*world uint32, zero before the first call) as mapped into THIS process (own rank
+ *                                  included).  The mapping itself (cudaIpc / VMM handles) is the caller's plumbing.
+ *   sequence  1, 2, 3, ... : the same value on every rank for the same step; consecutive calls on one stream.
+ *   local != out, both 16-byte aligned, count a multiple of 4.  Only enqueues work on cuda_stream. */
+size_t dirt_peer_exchange_bytes(int world, long long count);
+int dirt_peer_exchange(const float* local, float* out, void* const* peer_slots, void* const* peer_flags,
+                       int world, int rank, long long count, unsigned int sequence, void* cuda_stream);
+
 /* Number of kernels the last call on this thread launched (bench.py's gpu_launches). */
 int dirt_last_launch_count(void);
 

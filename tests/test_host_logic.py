@@ -34,7 +34,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), name
     L = _lib.lib()
-    assert L.dirt_abi_version() == 3
+    assert L.dirt_abi_version() == 4
     assert _lib.error_string(0) == 'ok'
     assert 'workspace' in _lib.error_string(-3)
     # workspace size is a pure function of the sizes and grows with them
