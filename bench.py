@@ -205,9 +205,10 @@ class PreparedStep:
         self.grad_background = torch.empty_like(self.background)
         # gradient of the batch-shared geometry: [V,4] | [V,C] in ONE flat buffer (what the all-reduce moves); two of
         # them alternate so that the all-reduce of step k overlaps the kernels of step k+1
-        self.shared_flat = [torch.zeros(V * (4 + C), dtype=torch.float32, device=device) for _ in range(2)]
+        self.flat_len = 4 * ((V * (4 + C) + 3) // 4)   # whole 16-byte words (the peer exchange moves float4s)
+        self.shared_flat = [torch.zeros(self.flat_len, dtype=torch.float32, device=device) for _ in range(2)]
         self.shared_gv = [f[:V * 4].view(V, 4) for f in self.shared_flat]
-        self.shared_gc = [f[V * 4:].view(V, C) for f in self.shared_flat]
+        self.shared_gc = [f[V * 4:V * (4 + C)].view(V, C) for f in self.shared_flat]
         self.ws_bytes = int(self.lib.dirt_workspace_bytes(B, H, W, C, V, F))
         self.workspace = torch.empty(self.ws_bytes, dtype=torch.uint8, device=device)
         self.launches_per_step = 0
@@ -228,7 +229,17 @@ class PreparedStep:
         if world > 1 and mode != 'nccl':
             try:
                 from dirt_b200.distributed import PeerExchange
-                self.peer = PeerExchange(V * width, self.device)
+                import torch.distributed as dist
+                failure = None
+                try:
+                    self.peer = PeerExchange(self.flat_len, self.device)
+                except Exception as e:
+                    failure = e
+                ok = torch.tensor([0.0 if failure is not None else 1.0], device=self.device)
+                dist.all_reduce(ok, op=dist.ReduceOp.MIN)   # one rank without the mapping: nobody uses it
+                if float(ok.item()) < 1.0:
+                    self.peer = None
+                    raise failure if failure is not None else RuntimeError('another rank could not map peer memory')
                 self.reduced_flat = [torch.zeros_like(f) for f in self.shared_flat]
                 self.collective = ('dirt_peer_exchange: [V,%d] fp32 gradient of the batch-shared geometry pushed into every peer\'s '
                                    'memory and summed in rank order, one kernel of %d CTAs per rank and step on a side stream, '
@@ -508,7 +519,18 @@ def run_ours(args):
         sampler.start()
         time.sleep(0.25)
     start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    token = torch.zeros(1, device=device)
+
+    def align_streams():
+        # The host leaves dist.barrier() up to ~1 ms apart across 8 ranks (measured: profiles/r02e_scale_n8_diagnostics.txt);
+        # a rank that starts early then waits, inside its timed region, for the late starter's first exchange.  A tiny
+        # all-reduce ENQUEUED on the stream (no host wait) completes on all ranks together: the start events that follow
+        # it in stream order are recorded within microseconds of each other, whatever the hosts do.
+        if world > 1:
+            dist.all_reduce(token)
+
     sync_all()
+    align_streams()
     start.record()
     launches = 0
     for _ in range(args.steps):
@@ -532,6 +554,7 @@ def run_ours(args):
         # all-reduce left out (all ranks still running at once), each as the list over ranks
         local_start, local_stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         sync_all()
+        align_streams()
         local_start.record()
         for _ in range(args.steps):
             prep.step(1)

@@ -60,9 +60,9 @@ class SharedVertexGrads:
     fill and what a single all-reduce moves."""
 
     def __init__(self, V, C, device=None, dtype=torch.float32):
-        self.flat = torch.zeros(V * (4 + C), dtype=dtype, device=device)
+        self.flat = torch.zeros(4 * ((V * (4 + C) + 3) // 4), dtype=dtype, device=device)   # whole 16-byte words
         self.grad_vertices = self.flat[:V * 4].view(V, 4)
-        self.grad_vertex_colors = self.flat[V * 4:].view(V, C)
+        self.grad_vertex_colors = self.flat[V * 4:V * (4 + C)].view(V, C)
 
     def all_reduce(self, group=None, stream=None):
         """Sums the buffer over all ranks.  With `stream` (CUDA) the collective is enqueued there after everything

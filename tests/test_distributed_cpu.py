@@ -66,9 +66,9 @@ def test_reduce_without_process_group():
 
 def test_shared_buffer_views_alias_one_allocation():
     shared = dd.SharedVertexGrads(7, 3)
-    assert shared.flat.numel() == 7 * 7
+    assert shared.flat.numel() == 52 and shared.flat.numel() % 4 == 0   # 7 * (4 + 3) = 49 floats, padded to whole 16-byte words
     shared.grad_vertices.fill_(1.0)
     shared.grad_vertex_colors.fill_(2.0)
-    assert float(shared.flat[:28].min()) == 1.0 and float(shared.flat[28:].min()) == 2.0
+    assert float(shared.flat[:28].min()) == 1.0 and float(shared.flat[28:49].min()) == 2.0 and float(shared.flat[49:].max()) == 0.0
     assert shared.grad_vertex_colors.data_ptr() % 16 == shared.grad_vertices.data_ptr() % 16
     assert shared.all_reduce() is None   # no process group: nothing to do
