@@ -60,10 +60,9 @@ namespace dirt {
 #ifndef DIRT_BWD_TMA
 #define DIRT_BWD_TMA 1
 #endif
-#ifndef DIRT_BWD_IMAGES
-#define DIRT_BWD_IMAGES 1       // consecutive images a warp walks at its tile position, the next image's halos requested (TMA)
-#endif                          // while the current one is processed.  Measured at cfg3: 1 -> 363 us, 2 / 4 / 8 -> 410 / 408 / 415 us
-                                // (profiles/r02_kbench_pipeline.txt): fewer, longer CTAs lose more than the prefetch wins
+// One image per warp.  A warp walking 2 / 4 / 8 consecutive images at its tile position with the next image's halos requested
+// (TMA) under the current one measured 410 / 408 / 415 us against 363 us at cfg3 (profiles/r02_kbench_pipeline.txt): fewer,
+// longer CTAs lose more than the prefetch wins.
 constexpr int TILE = 8;               // backward tile edge: one warp per 8x8 tile, two pixels per lane
 constexpr int HALO_ROWS = TILE + 2;   // 10
 constexpr int HALO_COLS = TILE + 4;   // 12: col-1 .. col+10 (one pixel around for the Scharr taps, two more to the right
@@ -485,7 +484,8 @@ __global__ void __launch_bounds__(NW * 32, DIRT_BWD_MIN_BLOCKS * DIRT_BWD_WARPS 
     int cs, int c0,   // cs: channels per pixel in the tensors, c0: first channel of the group this launch handles (width C)
     int gstride,      // floats per vertex row of grad_vertex_colors as this launch sees it (cs, or 4 for the padded rows of C = 3)
     int flags,        // BWD_SHARED_GEOMETRY: vertex gradients accumulated over the batch ([V,.]); BWD_SKIP_POSITION / _COLOUR
-    unsigned long long expect_tag)   // != 0: the caller promised that the workspace holds the setup records with this tag
+    unsigned long long expect_tag,   // != 0: the caller promised that the workspace holds the setup records with this tag
+    int b_base)                      // first image of this launch (the grid's z extent holds at most 65535 images)
 {
     using SM = BwdSmem<C, NSLOT>;
     constexpr int NS = C + 3;                  // scalars per pixel: C colour + (a,b,c)
@@ -501,88 +501,32 @@ __global__ void __launch_bounds__(NW * 32, DIRT_BWD_MIN_BLOCKS * DIRT_BWD_WARPS 
     // shuffles of the reduction need no re-convergence barriers.
     const int lane = threadIdx.x & 31;
     const int warp = (int)__reduce_min_sync(0xffffffffu, threadIdx.x >> 5);
-    const int tx = blockIdx.x * NW + warp, ty = blockIdx.y;
+    const int tx = blockIdx.x * NW + warp, ty = blockIdx.y, b = b_base + (int)blockIdx.z;
     if (tx >= d.btiles_x) return;
-    unsigned char* const sm = smem_raw + warp * SM::BYTES;
-    float* const tile = reinterpret_cast<float*>(sm + SM::PX_OFF);
-    int* const ids_tile = reinterpret_cast<int*>(sm + SM::IDS_OFF);
-    float4* const gbuf = reinterpret_cast<float4*>(sm + SM::GBUF_OFF);
-    SlotRec* const table = reinterpret_cast<SlotRec*>(sm + SM::TABLE_OFF);
-    int* const keys = reinterpret_cast<int*>(sm + SM::KEYS_OFF);
-    uint64_t* const bars = reinterpret_cast<uint64_t*>(sm + SM::BAR_OFF);   // [0]: face ids, [1]: pixels
-
+    const int H = d.H, W = d.W;
     const int trow0 = ty * TILE, tcol0 = tx * TILE;
     const int lcol = lane & 7, lrow0 = (lane >> 3) * 2;
     const int row0 = trow0 + lrow0, col = tcol0 + lcol;
-    const int H = d.H, W = d.W;
-    // this lane's cells: its two pixels and one cell of the 32-cell ring around the tile (corners are never read)
-    const int g0 = (lrow0 + 1) * GB_COLS + lcol + 1;                  // G-buffer tile index of pixel 0 (pixel 1: + GB_COLS)
-    const int ring_r = lane < 8 ? 0 : lane < 16 ? TILE + 1 : lane - (lane < 24 ? 15 : 23);
-    const int ring_c = lane < 8 ? lane + 1 : lane < 16 ? lane - 7 : lane < 24 ? 0 : TILE + 1;
-    // whole halo (12 columns: the flat-order reads reach two past the 10) inside the frame: no clamping, every pixel is
-    // interior.  (What a 16-wide TMA box holds beyond the halo may be out of bounds: zero-filled, never read.)
-    const bool inner = tcol0 >= 1 && trow0 >= 1 && tcol0 + HALO_COLS - 2 <= W - 1 && trow0 + TILE <= H - 1;
-    const bool use_tma = USE_TMA && inner;   // warp-uniform
-    const bool per_item = !(flags & BWD_SHARED_GEOMETRY);
     const bool want_pos = !(flags & BWD_SKIP_POSITION), want_col = !(flags & BWD_SKIP_COLOUR);
 
-    if (expect_tag != 0 && (blockIdx.x | blockIdx.y | blockIdx.z | threadIdx.x) == 0 && ws.header->tag != expect_tag) {
+    if (expect_tag != 0 && (blockIdx.x | blockIdx.y | (unsigned)b | threadIdx.x) == 0 && ws.header->tag != expect_tag) {
         // the workspace was not filled by a forward / visibility call on these (vertices, faces, sizes): flag it
         // (dirt_workspace_status) and poison the result instead of returning plausible numbers
         ws.header->error = 1;
         if (d.V > 0) grad_vertices[0] = __int_as_float(0x7fc00000);
     }
-    uint32_t parity_ids = 0, parity_px = 0;
-    if (USE_TMA) {
-        if (lane == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        __syncwarp();
-    }
 
-    // This warp walks DIRT_BWD_IMAGES consecutive images at its tile position.  Their tile flags are fetched together, and
-    // (TMA tiles) the face-id halo of the next flagged image is requested as soon as this image's ids sit in registers,
-    // its pixel halo as soon as this image's Scharr sums are done: the loads of image i+1 fly under the work on image i.
-    const int b_first = blockIdx.z * DIRT_BWD_IMAGES;
-    const int n_img = min(DIRT_BWD_IMAGES, d.B - b_first);
-    unsigned flagmask;
+    // ---- what every tile needs: the forward pass's coverage flag of its 16x8 tile and grad_pixels of this lane's pixels.
+    // Nearly half of a frame's tiles end right here, so nothing else is set up before the flag is known.
+    bool flagged;
     {
         bool f = false;
-        if (lane < n_img) f = tile_flags == nullptr || tile_flags[(size_t)(b_first + lane) * d.tiles + ty * d.tiles_x + (tx >> 1)] != 0;
-        flagmask = __ballot_sync(0xffffffffu, f);
+        if (lane == 0) f = tile_flags == nullptr || tile_flags[(size_t)b * d.tiles + ty * d.tiles_x + (tx >> 1)] != 0;
+        flagged = (__ballot_sync(0xffffffffu, f) & 1u) != 0u;   // through a vote: known to be warp-uniform
     }
-    int ids_issued = -1, px_issued = -1;   // image (index in this warp's run) whose halos are already on their way
-    const auto issue_ids = [&](int bi) {
-        if (lane == 0) {
-            fence_proxy_async();
-            mbar_expect_tx(&bars[0], SM::IDS_BYTES);
-            tma_load_3d(ids_tile, &ids_map, tcol0 - 1 - IDS_COL0, trow0 - 1, b_first + bi, &bars[0]);
-        }
-        ids_issued = bi;
-    };
-    const auto issue_px = [&](int bi) {
-        if (lane == 0) {
-            fence_proxy_async();
-            mbar_expect_tx(&bars[1], SM::PX_BYTES);
-            tma_load_3d(tile, &px_map, (tcol0 - 1 - PxTile<C>::COL0) * C, trow0 - 1, b_first + bi, &bars[1]);
-        }
-        px_issued = bi;
-    };
-
-    for (int bi = 0; bi < n_img; ++bi) {
-    const int b = b_first + bi;
-    const TriInterp* itp_b = ws.itp + (size_t)b * d.F;
-    const TriXY* xy_b = ws.xy + (size_t)b * d.F;
-    float* gverts = grad_vertices + (size_t)(per_item ? b : 0) * d.V * 4;
-    float* gcols = grad_vertex_colors + (size_t)(per_item ? b : 0) * d.V * gstride + c0;
     const size_t img = (size_t)b * H * W;
     const size_t p0 = img + (size_t)row0 * W + col;   // pixel 0 of this lane (pixel 1: + W)
     const bool in0 = col < W && row0 < H, in1 = col < W && row0 + 1 < H;
-    // the next flagged image of this warp's run (n_img: none)
-    const unsigned later = flagmask & ~((2u << bi) - 1u);
-    const int nb = later ? __ffs(later) - 1 : n_img;
-
-    const bool flagged = (flagmask >> bi) & 1u;
-    // ---- grad_pixels of this lane's pixels: needed on every other path, so the loads go out first
     float gp[2][C];
 #pragma unroll
     for (int pix = 0; pix < 2; ++pix) {
@@ -598,34 +542,6 @@ __global__ void __launch_bounds__(NW * 32, DIRT_BWD_MIN_BLOCKS * DIRT_BWD_WARPS 
             for (int ch = 0; ch < C; ++ch) gp[pix][ch] = __ldg(grad_pixels + p * cs + c0 + ch);
         }
     }
-
-    // ---- (1) stage the halo of face ids and pixels (unless they were requested while the previous image was processed)
-    if (flagged) {
-        if (use_tma) {
-            if (ids_issued != bi) issue_ids(bi);
-            if (want_pos && px_issued != bi) issue_px(bi);
-        } else {
-            for (int e = lane; e < HALO_ROWS * HALO_COLS; e += 32) {
-                const int hr = e / HALO_COLS, hc = e - hr * HALO_COLS;
-                const int r = trow0 - 1 + hr, c = tcol0 - 1 + hc;
-                int* const id_dst = ids_tile + hr * IDS_COLS + hc + IDS_COL0;
-                if (r >= 0 && r < H && c >= 0 && c < W) cp_async_4(id_dst, face_ids + img + (size_t)r * W + c);
-                else *id_dst = -1;
-                if (!want_pos) continue;
-                const int rc = max(0, min(H - 1, r)), cc = max(0, min(W - 1, c));
-                const float* src = pixels + (img + (size_t)rc * W + cc) * cs + c0;
-                float* const px_dst = tile + (hr * PxTile<C>::COLS + hc + PxTile<C>::COL0) * C;
-                if (C == 4) cp_async_16(px_dst, src);
-                else {
-#pragma unroll
-                    for (int ch = 0; ch < C; ++ch) cp_async_4(px_dst + ch, src + ch);
-                }
-            }
-            cp_async_commit();
-        }
-        if (lane < NSLOT) keys[lane] = -1;
-    }
-
     auto store_gb = [&](int pix, bool uncovered) {
         // grad_background: grad_pixels where uncovered, 0 elsewhere (:143-148, memset :247)
         const size_t p = p0 + (size_t)pix * W;
@@ -641,29 +557,81 @@ __global__ void __launch_bounds__(NW * 32, DIRT_BWD_MIN_BLOCKS * DIRT_BWD_WARPS 
         // the forward pass flagged every 16x8 tile that shows a face or touches one that does: nothing can reach this one
         if (want_col && in0) store_gb(0, true);
         if (want_col && in1) store_gb(1, true);
-        continue;
+        return;
     }
 
+    // ---- a tile a face may reach: its slice of shared memory, the ring cell of this lane, the staging mode
+    unsigned char* const sm = smem_raw + warp * SM::BYTES;
+    float* const tile = reinterpret_cast<float*>(sm + SM::PX_OFF);
+    int* const ids_tile = reinterpret_cast<int*>(sm + SM::IDS_OFF);
+    float4* const gbuf = reinterpret_cast<float4*>(sm + SM::GBUF_OFF);
+    SlotRec* const table = reinterpret_cast<SlotRec*>(sm + SM::TABLE_OFF);
+    int* const keys = reinterpret_cast<int*>(sm + SM::KEYS_OFF);
+    uint64_t* const bars = reinterpret_cast<uint64_t*>(sm + SM::BAR_OFF);   // [0]: face ids, [1]: pixels
+    // this lane's cells: its two pixels and one cell of the 32-cell ring around the tile (corners are never read)
+    const int g0 = (lrow0 + 1) * GB_COLS + lcol + 1;                  // G-buffer tile index of pixel 0 (pixel 1: + GB_COLS)
+    const int ring_r = lane < 8 ? 0 : lane < 16 ? TILE + 1 : lane - (lane < 24 ? 15 : 23);
+    const int ring_c = lane < 8 ? lane + 1 : lane < 16 ? lane - 7 : lane < 24 ? 0 : TILE + 1;
+    // whole halo (12 columns: the flat-order reads reach two past the 10) inside the frame: no clamping, every pixel is
+    // interior.  (What a 16-wide TMA box holds beyond the halo may be out of bounds: zero-filled, never read.)
+    const bool inner = tcol0 >= 1 && trow0 >= 1 && tcol0 + HALO_COLS - 2 <= W - 1 && trow0 + TILE <= H - 1;
+    const bool use_tma = USE_TMA && inner;   // warp-uniform
+    const bool per_item = !(flags & BWD_SHARED_GEOMETRY);
+    const TriInterp* itp_b = ws.itp + (size_t)b * d.F;
+    const TriXY* xy_b = ws.xy + (size_t)b * d.F;
+    float* gverts = grad_vertices + (size_t)(per_item ? b : 0) * d.V * 4;
+    float* gcols = grad_vertex_colors + (size_t)(per_item ? b : 0) * d.V * gstride + c0;
+
+    // ---- (1) stage the halo of face ids and pixels: TMA (one elected lane, one mbarrier each) or per-lane cp.async
+    if (use_tma) {
+        if (lane == 0) {
+            mbar_init(&bars[0], 1); mbar_init(&bars[1], 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            fence_proxy_async();
+            mbar_expect_tx(&bars[0], SM::IDS_BYTES);
+            tma_load_3d(ids_tile, &ids_map, tcol0 - 1 - IDS_COL0, trow0 - 1, b, &bars[0]);
+            if (want_pos) {
+                mbar_expect_tx(&bars[1], SM::PX_BYTES);
+                tma_load_3d(tile, &px_map, (tcol0 - 1 - PxTile<C>::COL0) * C, trow0 - 1, b, &bars[1]);
+            }
+        }
+        __syncwarp();   // the barriers exist before any lane waits on them
+    } else {
+        for (int e = lane; e < HALO_ROWS * HALO_COLS; e += 32) {
+            const int hr = e / HALO_COLS, hc = e - hr * HALO_COLS;
+            const int r = trow0 - 1 + hr, c = tcol0 - 1 + hc;
+            int* const id_dst = ids_tile + hr * IDS_COLS + hc + IDS_COL0;
+            if (r >= 0 && r < H && c >= 0 && c < W) cp_async_4(id_dst, face_ids + img + (size_t)r * W + c);
+            else *id_dst = -1;
+            if (!want_pos) continue;
+            const int rc = max(0, min(H - 1, r)), cc = max(0, min(W - 1, c));
+            const float* src = pixels + (img + (size_t)rc * W + cc) * cs + c0;
+            float* const px_dst = tile + (hr * PxTile<C>::COLS + hc + PxTile<C>::COL0) * C;
+            if (C == 4) cp_async_16(px_dst, src);
+            else {
+#pragma unroll
+                for (int ch = 0; ch < C; ++ch) cp_async_4(px_dst + ch, src + ch);
+            }
+        }
+        cp_async_commit();
+    }
+    if (lane < NSLOT) keys[lane] = -1;
+
     // ---- (2) face ids -> slots of the tile's face table ---------------------------------------------------------------
-    if (use_tma) { mbar_wait(&bars[0], parity_ids); parity_ids ^= 1; }
+    if (use_tma) mbar_wait(&bars[0], 0);
     else cp_async_wait_all();
     __syncwarp();
     const int i0 = (lrow0 + 1) * IDS_COLS + lcol + 1 + IDS_COL0;
     const int id0 = ids_tile[i0], id1 = ids_tile[i0 + IDS_COLS], idr = ids_tile[ring_r * IDS_COLS + ring_c + IDS_COL0];
     if (want_col && in0) store_gb(0, id0 < 0);
     if (want_col && in1) store_gb(1, id1 < 0);
-    // neighbours in the visibility buffer (the id tile is about to be handed to the next image)
+    // neighbours in the visibility buffer
     const int up0 = ids_tile[i0 - IDS_COLS], l0 = ids_tile[i0 - 1], r0 = ids_tile[i0 + 1];
     const int l1 = ids_tile[i0 + IDS_COLS - 1], r1 = ids_tile[i0 + IDS_COLS + 1], dn1 = ids_tile[i0 + 2 * IDS_COLS];
-    __syncwarp();
-    if (use_tma && nb < n_img) issue_ids(nb);
     if (!__any_sync(0xffffffffu, (id0 & id1 & idr) >= 0)) {
-        // no face in the tile or its ring
-        if (use_tma && want_pos) {
-            mbar_wait(&bars[1], parity_px); parity_px ^= 1;
-            if (nb < n_img) issue_px(nb);
-        }
-        continue;
+        // no face in the tile or its ring (the pixel halo must still land before the warp gives up its shared memory)
+        if (use_tma && want_pos) mbar_wait(&bars[1], 0);
+        return;
     }
     // per pixel: covered, or (interior pixels only) a covered 4-neighbour that could dilate into it
     bool near0, near1, interior0 = true, interior1 = true;
@@ -701,13 +669,9 @@ __global__ void __launch_bounds__(NW * 32, DIRT_BWD_MIN_BLOCKS * DIRT_BWD_WARPS 
     __syncwarp();
     if (__any_sync(0xffffffffu, overflow)) {
         // more distinct faces than slots: the reference-shaped path for this tile
-        if (use_tma && want_pos) {
-            mbar_wait(&bars[1], parity_px); parity_px ^= 1;
-            if (nb < n_img) issue_px(nb);
-        }
+        if (use_tma && want_pos) mbar_wait(&bars[1], 0);
         tile_generic<C>(vertices, pixels, grad_pixels, face_ids, gverts, gcols, itp_b, Frame{d.B, H, W}, d.V, b, col, row0, cs, c0, gstride, want_pos, want_col);
-        __syncwarp();
-        continue;
+        return;
     }
     // fill the table: the lane whose index is an occupied slot copies that face's 96 bytes
     {
@@ -726,8 +690,8 @@ __global__ void __launch_bounds__(NW * 32, DIRT_BWD_MIN_BLOCKS * DIRT_BWD_WARPS 
 
     // ---- (3) G-buffer tile: this lane's two pixels and its ring cell ---------------------------------------------------
     cp_async_wait_all();
-    if (use_tma && want_pos) { mbar_wait(&bars[1], parity_px); parity_px ^= 1; }
-    __syncwarp();   // table and pixel halo complete; every lane has read its face ids (the G-buffer tile reuses their bytes)
+    if (use_tma && want_pos) mbar_wait(&bars[1], 0);
+    __syncwarp();   // table and pixel halo complete
     const float inf = __int_as_float(0x7f800000);
     float4 own[2];
     own[0] = make_float4(-1.f, -1.f, -1.f, inf);
@@ -872,10 +836,6 @@ __global__ void __launch_bounds__(NW * 32, DIRT_BWD_MIN_BLOCKS * DIRT_BWD_WARPS 
         }
     }
 
-    // the pixel halo has served this image: hand its buffer to the next one while the reduction runs
-    __syncwarp();
-    if (use_tma && want_pos && nb < n_img) issue_px(nb);
-
     // ---- (4) per-face reduction -----------------------------------------------------------------------------------------
     // One iteration per occupied slot: the 3*(C+3) sums of the face are reduced over the 32 lanes with a transposed
     // butterfly (each lane ends up owning one finished sum) and leave the SM as ONE warp-wide RED.  Faces that own only a
@@ -970,8 +930,6 @@ __global__ void __launch_bounds__(NW * 32, DIRT_BWD_MIN_BLOCKS * DIRT_BWD_WARPS 
 #endif
     }
 #endif
-    __syncwarp();   // the next image's staging overwrites the tile buffers
-    }   // bi
 }
 
 // grad_vertex_colors of a 3-channel launch is accumulated in 16-byte rows (one vector RED per vertex instead of three
@@ -1028,10 +986,11 @@ static cudaError_t launch_tile_kernel(const CUtensorMap& px_map, const CUtensorM
         if (e != cudaSuccess) return e;
         configured = true;
     }
-    // z: runs of DIRT_BWD_IMAGES consecutive images (a batch beyond 65535 runs would need a second grid dimension)
-    const dim3 grid((unsigned)((d.btiles_x + NW - 1) / NW), (unsigned)d.btiles_y, (unsigned)((d.B + DIRT_BWD_IMAGES - 1) / DIRT_BWD_IMAGES));
-    kernel<<<grid, NW * 32, smem, stream>>>(px_map, ids_map, vertices, pixels, grad_pixels, face_ids, grad_background,
-                                            grad_vertices, grad_vertex_colors, ws, d, tflags, cs, c0, gstride, flags, expect_tag);
+    for (int b_base = 0; b_base < d.B; b_base += 65535) {   // z: image
+        const dim3 grid((unsigned)((d.btiles_x + NW - 1) / NW), (unsigned)d.btiles_y, (unsigned)min(d.B - b_base, 65535));
+        kernel<<<grid, NW * 32, smem, stream>>>(px_map, ids_map, vertices, pixels, grad_pixels, face_ids, grad_background,
+                                                grad_vertices, grad_vertex_colors, ws, d, tflags, cs, c0, gstride, flags, expect_tag, b_base);
+    }
     return cudaGetLastError();
 }
 
