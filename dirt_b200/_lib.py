@@ -42,6 +42,8 @@ def lib():
     L.dirt_last_launch_count.restype = i
     L.dirt_workspace_bytes.restype = sz
     L.dirt_workspace_bytes.argtypes = [i] * 6
+    L.dirt_workspace_bytes_min.restype = sz
+    L.dirt_workspace_bytes_min.argtypes = [i] * 6
     L.dirt_rasterise_forward.restype = i
     L.dirt_rasterise_forward.argtypes = [vp] * 6 + [i] * 6 + [vp, sz, vp]
     L.dirt_rasterise_backward.restype = i
@@ -63,7 +65,7 @@ def lib():
     return _lib
 
 
-EXPORTED_SYMBOLS = ['dirt_error_string', 'dirt_abi_version', 'dirt_workspace_bytes', 'dirt_rasterise_forward',
+EXPORTED_SYMBOLS = ['dirt_error_string', 'dirt_abi_version', 'dirt_workspace_bytes', 'dirt_workspace_bytes_min', 'dirt_rasterise_forward',
                     'dirt_rasterise_backward', 'dirt_rasterise_backward_ex', 'dirt_workspace_status',
                     'dirt_rasterise_visibility', 'dirt_peer_exchange_bytes', 'dirt_peer_exchange', 'dirt_last_launch_count',
                     'dirt_kernel_timer_enable', 'dirt_kernel_timer_elapsed_ms']

@@ -111,11 +111,21 @@ static int make_groups(int C, const int* channel_groups, int n_groups, GroupSpec
     return DIRT_OK;
 }
 
-static int check_workspace(void* workspace, size_t workspace_bytes, int B, int H, int W, int C, int V, int F)
+extern "C" size_t dirt_workspace_bytes_min(int B, int H, int W, int C, int V, int F)
+{
+    if (!shape_ok(B, H, W, C > 0 ? C : 1, V, F)) return 0;
+    Workspace ws = carve_workspace(nullptr, B, H, W, C, V, F);
+    return ws.bytes_without_face_ids + 256;
+}
+
+// needs_face_id_scratch: only a backward call without face ids derives them into the workspace's last block
+static int check_workspace(void* workspace, size_t workspace_bytes, int B, int H, int W, int C, int V, int F,
+                           bool needs_face_id_scratch = false)
 {
     if (!workspace) return DIRT_ERR_NULL_POINTER;
     if ((uintptr_t)workspace % 256 != 0) return DIRT_ERR_MISALIGNED;
-    if (workspace_bytes < dirt_workspace_bytes(B, H, W, C, V, F)) return DIRT_ERR_WORKSPACE_TOO_SMALL;
+    const size_t need = needs_face_id_scratch ? dirt_workspace_bytes(B, H, W, C, V, F) : dirt_workspace_bytes_min(B, H, W, C, V, F);
+    if (workspace_bytes < need) return DIRT_ERR_WORKSPACE_TOO_SMALL;
     return DIRT_OK;
 }
 
@@ -194,7 +204,7 @@ static int backward_impl(const float* vertices, const int32_t* faces, const floa
     if ((uintptr_t)pixels % 4 || (uintptr_t)grad_pixels % 4 || (uintptr_t)grad_background % 4 ||
         (uintptr_t)grad_vertex_colors % 4 || (uintptr_t)faces % 4 || (uintptr_t)face_ids % 4)
         return DIRT_ERR_MISALIGNED;
-    rc = check_workspace(workspace, workspace_bytes, B, H, W, C, V, F);
+    rc = check_workspace(workspace, workspace_bytes, B, H, W, C, V, F, face_ids == nullptr);
     if (rc != DIRT_OK) return rc;
     cudaStream_t stream = (cudaStream_t)cuda_stream;
     const Workspace ws = carve_workspace(workspace, B, H, W, C, V, F);

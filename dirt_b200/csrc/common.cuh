@@ -107,9 +107,10 @@ struct Workspace {
     int* bins;            // [B*T*BIN_CAP]
     int2* ovf;            // [B*tiles_y*OVF_ROW_CAP]  (tile, face)
     struct Header* header; // identity of the (vertices, faces, sizes) the setup records belong to; error flag
-    int32_t* face_ids;    // [B*H*W] (used when the caller does not supply a buffer)
+    int32_t* face_ids;    // [B*H*W] (last block; used only by a backward call without face ids)
     float* gc_pad;        // [B*V*4] (C == 3 only) grad_vertex_colors accumulated in 16-byte rows: one vector RED per vertex
     size_t zero_bytes;    // bytes from tile_count that the forward pass zeroes (counts, flags, list counts, header)
+    size_t bytes_without_face_ids;
     size_t bytes;
 };
 
@@ -139,8 +140,9 @@ inline Workspace carve_workspace(void* base, int B, int H, int W, int C, int V, 
     ws.large_list = (int*)take(BF * sizeof(int));
     ws.bins = (int*)take(BT * BIN_CAP * sizeof(int));
     ws.ovf = (int2*)take(rows * OVF_ROW_CAP * sizeof(int2));
-    ws.face_ids = (int32_t*)take((size_t)B * H * W * sizeof(int32_t));
     ws.gc_pad = (float*)take(C == 3 ? (size_t)B * V * 4 * sizeof(float) : 0);
+    ws.bytes_without_face_ids = off;   // all a call needs whose caller holds the face ids (dirt_workspace_bytes_min)
+    ws.face_ids = (int32_t*)take((size_t)B * H * W * sizeof(int32_t));
     ws.bytes = off;
     return ws;
 }

@@ -51,7 +51,7 @@ class HostRasteriser:
         self.h_out = {k: torch.empty(self.d[k].shape, dtype=self.d[k].dtype).pin_memory()
                       for k in ('pixels', 'grad_background', 'grad_vertices', 'grad_vertex_colors')}
         nmax = max(e - b for b, e in self.bounds)
-        self.ws_bytes = int(self.lib.dirt_workspace_bytes(nmax, H, W, C, V, F))
+        self.ws_bytes = int(self.lib.dirt_workspace_bytes_min(nmax, H, W, C, V, F))   # the backward calls are handed the face ids
         # one workspace per chunk in flight (the backward call reuses the forward's setup records)
         self.ws = [torch.empty(self.ws_bytes, dtype=torch.uint8, device=dev) for _ in range(self.chunks)]
         self.s_in, self.s_run, self.s_out = (torch.cuda.Stream(dev) for _ in range(3))

@@ -41,13 +41,16 @@ def _ptr(t):
     return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
 
 
-def _workspace(B, H, W, C, V, F, device):
-    nbytes = _lib.lib().dirt_workspace_bytes(B, H, W, C, V, F)
-    # the allocation also covers a 3-channel call on the same geometry (its workspace carries padded gradient rows at
-    # the end, everything before is laid out independently of C): deferred shading hands the G-buffer pass's workspace
-    # to the backward call on the shaded, usually 3-channel, image
-    alloc = max(int(nbytes), int(_lib.lib().dirt_workspace_bytes(B, H, W, 3, V, F)), 256)
-    return torch.empty(alloc, dtype=torch.uint8, device=device), int(nbytes)
+def _workspace(B, H, W, C, V, F, device, face_id_scratch=False):
+    """A workspace for one call -> (tensor, its size).  Without `face_id_scratch` it is the smaller size that serves every
+    call whose caller holds the face ids (dirt_workspace_bytes_min: no B*H*W*4-byte block for deriving them), which is every
+    call this module makes except a backward call without `face_ids`."""
+    size = _lib.lib().dirt_workspace_bytes if face_id_scratch else _lib.lib().dirt_workspace_bytes_min
+    # the allocation also covers a 3-channel call on the same geometry (its workspace carries padded gradient rows behind
+    # the blocks that are laid out independently of C): deferred shading hands the G-buffer pass's workspace to the backward
+    # call on the shaded, usually 3-channel, image
+    alloc = max(int(size(B, H, W, C, V, F)), int(size(B, H, W, 3, V, F)), 256)
+    return torch.empty(alloc, dtype=torch.uint8, device=device), alloc
 
 
 def _require_cuda(*tensors):
@@ -129,10 +132,11 @@ def rasterise_backward_raw(vertices, faces, pixels, grad_pixels, face_ids=None, 
     else:
         groups_arr = (ctypes.c_int * len(channel_groups))(*[int(g) for g in channel_groups])
         groups_ptr, n_groups = groups_arr, len(channel_groups)
-    nbytes = int(_lib.lib().dirt_workspace_bytes(B, H, W, C, V, F))
-    reuse = int(setup_workspace is not None and face_ids is not None and setup_workspace.numel() >= nbytes and
+    need = int(_lib.lib().dirt_workspace_bytes_min(B, H, W, C, V, F))
+    reuse = int(setup_workspace is not None and face_ids is not None and setup_workspace.numel() >= need and
                 getattr(setup_workspace, '_dirt_setup_of', None) == _geometry_identity(vertices, faces, H, W))
-    ws = setup_workspace if reuse else _workspace(B, H, W, C, V, F, device)[0]
+    ws = setup_workspace if reuse else _workspace(B, H, W, C, V, F, device, face_id_scratch=face_ids is None)[0]
+    nbytes = int(ws.numel())
     flags = ((_lib.BWD_SHARED_GEOMETRY if shared_geometry else 0) | (0 if want_position else _lib.BWD_SKIP_POSITION) |
              (0 if want_colour else _lib.BWD_SKIP_COLOUR))
     with torch.cuda.device(device):
@@ -147,7 +151,7 @@ def rasterise_backward_raw(vertices, faces, pixels, grad_pixels, face_ids=None, 
 def workspace_status(workspace, B, H, W, C, V, F):
     """dirt_workspace_status: waits for the stream; raises if a backward call was handed a workspace that did not hold
     the setup records it was promised (csrc/api.cu)."""
-    nbytes = int(_lib.lib().dirt_workspace_bytes(B, H, W, C, V, F))
+    nbytes = int(workspace.numel())
     with torch.cuda.device(workspace.device):
         rc = _lib.lib().dirt_workspace_status(_ptr(workspace), nbytes, B, H, W, C, V, F, _stream_ptr(workspace.device))
     _lib.check(rc, 'RasteriseGrad')

@@ -63,6 +63,10 @@ int dirt_abi_version(void);
  * triangle records + bounded per-tile reference lists + per-tile counters. */
 size_t dirt_workspace_bytes(int B, int H, int W, int C, int V, int F);
 
+/* The same without the B*H*W*4-byte block that only a backward call WITHOUT face ids uses (it derives them there):
+ * enough for forward, visibility, and every backward call that is handed the forward's face ids. */
+size_t dirt_workspace_bytes_min(int B, int H, int W, int C, int V, int F);
+
 /* Forward: pixels = rasterise(background, vertices, vertex_colors, faces).
  * Handles any C >= 1 in one pass (the reference runs one op per channel group of 3 or 1,
  * rasterise_ops.py:86-108; the forward result does not depend on the grouping).

@@ -42,6 +42,9 @@ def test_library_exports_every_declared_symbol():
     b = L.dirt_workspace_bytes(2, 64, 64, 3, 100, 200)
     assert 0 < a < b
     assert L.dirt_workspace_bytes(1, 0, 64, 3, 100, 200) == 0
+    # the smaller size leaves out exactly the face-id scratch block (B*H*W int32, 256-byte granules)
+    assert a - L.dirt_workspace_bytes_min(1, 64, 64, 3, 100, 200) == 64 * 64 * 4
+    assert L.dirt_workspace_bytes_min(1, 0, 64, 3, 100, 200) == 0
 
 
 def test_argument_validation_without_a_gpu():
@@ -78,6 +81,24 @@ def test_c_abi_rejects_bad_arguments():
                                      null) == _lib.ERR_BAD_CHANNEL_GROUPS
     assert L.dirt_rasterise_backward(null, null, null, null, null, null, null, null, 1, 8, 8, 3, (1 << 24) + 1, 2, None, 0,
                                      0, null, 0, null) == _lib.ERR_TOO_MANY_VERTICES
+    # a backward call without face ids needs the full workspace, one with face ids the smaller one (checked before any
+    # pointer is touched: the addresses below are never dereferenced)
+    p = lambda a: ctypes.c_void_p(a)
+    small, full = L.dirt_workspace_bytes_min(1, 8, 8, 3, 4, 2), L.dirt_workspace_bytes(1, 8, 8, 3, 4, 2)
+    assert small < full
+    args = lambda ids, nbytes: (p(4096), p(4096), p(4096), p(4096), ids, p(4096), p(4096), p(4096), 1, 8, 8, 3, 4, 2, None, 0, 0,
+                                p(4096), nbytes, null)
+    assert L.dirt_rasterise_backward(*args(null, small)) == _lib.ERR_WORKSPACE_TOO_SMALL
+    assert L.dirt_rasterise_backward(*args(p(4096), small - 1)) == _lib.ERR_WORKSPACE_TOO_SMALL
+    # the peer exchange validates its arguments before it launches anything
+    assert L.dirt_peer_exchange_bytes(8, 20496) == 2 * 8 * 20496 * 4 and L.dirt_peer_exchange_bytes(17, 4) == 0
+    two = (ctypes.c_void_p * 2)(p(4096), p(4096))
+    assert L.dirt_peer_exchange(p(4096), p(8192), two, two, 2, 0, 6, 1, null) == _lib.ERR_BAD_SHAPE      # count % 4
+    assert L.dirt_peer_exchange(p(4096), p(4096), two, two, 2, 0, 8, 1, null) == _lib.ERR_BAD_SHAPE      # local == out
+    assert L.dirt_peer_exchange(p(4096), p(8192), two, two, 2, 2, 8, 1, null) == _lib.ERR_BAD_SHAPE      # rank >= world
+    assert L.dirt_peer_exchange(p(4096), p(8192), two, two, 2, 0, 8, 0, null) == _lib.ERR_BAD_SHAPE      # sequence 0
+    assert L.dirt_peer_exchange(p(4100), p(8192), two, two, 2, 0, 8, 1, null) == _lib.ERR_MISALIGNED
+    assert L.dirt_peer_exchange(null, p(8192), two, two, 2, 0, 8, 1, null) == _lib.ERR_NULL_POINTER
     # B == 0 is a no-op, as an empty batch is for the reference
     assert L.dirt_rasterise_forward(null, null, null, null, null, null, 0, 8, 8, 3, 4, 2, null, 0, null) == 0
     # channel counts whose greedy split into groups of 3 and 1 would not fit the group table are a shape error up front
