@@ -8,8 +8,12 @@ A "step" is one forward + one backward pass of the hot path over one batch of sy
 (BASELINE cfg3 by default: batch 64 per GPU, 512x512, 4-channel G-buffer, 5120-triangle icosphere with a
 pose per item), called through the C ABI of libdirt_b200.so with every buffer already resident in HBM,
 with the vertex gradients accumulated over the batch inside the backward kernel (DIRT_BWD_SHARED_GEOMETRY: one
-[V, 4+C] buffer) and -- when N > 1 -- ONE NCCL all-reduce of that buffer per step, issued on a side stream so that it
+[V, 4+C] buffer) and -- when N > 1 -- ONE sum of that buffer over the ranks per step: the library's peer-memory kernel
+(dirt_peer_exchange; --collective nccl / the automatic fallback: NCCL's all-reduce), issued on a side stream so that it
 overlaps the next step's forward pass (the batch shards over GPUs with no other exchange: weak scaling, 64 images per GPU).
+The timed region is bracketed by barrier + synchronize on both sides; the start events are additionally aligned on the
+device (a one-element all-reduce enqueued before them), and `multi_gpu` in the JSON line lists every rank's time with and
+without the exchange.
 
 One JSON line on rank 0:  value = B_total*H*W / step time (CUDA events, max over ranks);  e2e = the same
 call with HOST (pinned) buffers, host<->device copies inside the timed region;  roofline = the dominant
