@@ -822,7 +822,7 @@ def main():
                     help='N>1: sum of the shared-geometry gradient over ranks by the library\'s peer-memory kernel (peer), by NCCL '
                          '(nccl), or the first that is available (auto)')
     ap.add_argument('--no-graph', action='store_true', help='launch every step call by call instead of replaying a CUDA graph')
-    ap.add_argument('--e2e-chunks', type=int, default=8, help='batch chunks of the host copy/compute pipeline')
+    ap.add_argument('--e2e-chunks', type=int, default=12, help='batch chunks of the host copy/compute pipeline')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-numpy-baseline', action='store_true', help='skip the numpy variants of the CPU baseline')
     ap.add_argument('--check', action='store_true', help='after timing, validate the benched buffers against the CPU oracle ("checked": true)')

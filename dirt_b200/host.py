@@ -5,9 +5,11 @@ transfers around it.  `HostRasteriser` hides them: the batch is cut into chunks 
 (copy-in, compute, copy-out) are chained with events, so the host->device copy of chunk i+1, the kernels of
 chunk i and the device->host copy of chunk i-1 overlap (PCIe is full duplex; the kernels are ~1 % of the
 transfer time).  Each chunk is one dirt_rasterise_forward + one dirt_rasterise_backward call on slices of
-preallocated device buffers.  Geometry (vertices, colours, faces) is small next to the images and goes up once per step;
-the chunks carry the two image tensors each way.  Measured at BASELINE cfg3 on a B200: 12.9 ms per step against 11.1 ms
-for the same transfers with no kernels at all (bench.py, `e2e`).
+preallocated device buffers; the forward call waits for the chunk's background only, the backward call for its
+grad_pixels, and each result is sent down as soon as its kernel has finished.  Geometry (vertices, colours, faces) is small next to the images and goes up once per step;
+the chunks carry the two image tensors each way.  Measured at BASELINE cfg3 on a B200 with 12 chunks: 12.4 ms per step against 11.2 ms
+for the same transfers with no kernels at all (bench.py, `e2e`; 13.2 ms before the two calls of a chunk waited for their
+own upload only, profiles/r02_e2e_chunks_split_waits.txt).
 """
 import ctypes
 
@@ -24,7 +26,7 @@ class HostRasteriser:
     of the shapes given at construction.  Results are valid after the returned event / `synchronize()`.
     """
 
-    def __init__(self, B, H, W, C, V, F, device=None, chunks=8):
+    def __init__(self, B, H, W, C, V, F, device=None, chunks=12):
         self.lib = _lib.lib()
         self.device = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
         self.shape = (B, H, W, C, V, F)
@@ -80,31 +82,42 @@ class HostRasteriser:
                 d[k].copy_(host_in[k], non_blocking=True)
         for i, (b0, b1) in enumerate(self.bounds):
             n = b1 - b0
+            stream = ctypes.c_void_p(self.s_run.cuda_stream)
+            # The forward call needs the background only and the backward call grad_pixels only: each kernel starts as soon
+            # as ITS upload has landed and each result goes down as soon as ITS kernel is done, so what cannot overlap
+            # anything at the two ends of the pipeline is half a chunk, not a whole one.
             with torch.cuda.stream(self.s_in):
-                for k in ('background', 'grad_pixels'):
-                    d[k][b0:b1].copy_(host_in[k][b0:b1], non_blocking=True)
-                ev_in = torch.cuda.Event()
-                ev_in.record(self.s_in)
+                d['background'][b0:b1].copy_(host_in['background'][b0:b1], non_blocking=True)
+                ev_bg = torch.cuda.Event()
+                ev_bg.record(self.s_in)
+                d['grad_pixels'][b0:b1].copy_(host_in['grad_pixels'][b0:b1], non_blocking=True)
+                ev_gp = torch.cuda.Event()
+                ev_gp.record(self.s_in)
             with torch.cuda.stream(self.s_run):
-                self.s_run.wait_event(ev_in)
-                stream = ctypes.c_void_p(self.s_run.cuda_stream)
+                self.s_run.wait_event(ev_bg)
                 rc = self.lib.dirt_rasterise_forward(
                     self._p(d['background'][b0:b1]), self._p(d['vertices'][b0:b1]), self._p(d['vertex_colors'][b0:b1]),
                     self._p(d['faces'][b0:b1]), self._p(d['pixels'][b0:b1]), self._p(d['face_ids'][b0:b1]),
                     n, H, W, C, V, F, self._p(self.ws[i]), self.ws_bytes, stream)
                 _lib.check(rc, 'Rasterise')
+                ev_fwd = torch.cuda.Event()
+                ev_fwd.record(self.s_run)
+            with torch.cuda.stream(self.s_out):
+                self.s_out.wait_event(ev_fwd)
+                self.h_out['pixels'][b0:b1].copy_(d['pixels'][b0:b1], non_blocking=True)
+            with torch.cuda.stream(self.s_run):
+                self.s_run.wait_event(ev_gp)
                 rc = self.lib.dirt_rasterise_backward(
                     self._p(d['vertices'][b0:b1]), self._p(d['faces'][b0:b1]), self._p(d['pixels'][b0:b1]),
                     self._p(d['grad_pixels'][b0:b1]), self._p(d['face_ids'][b0:b1]), self._p(d['grad_background'][b0:b1]),
                     self._p(d['grad_vertices'][b0:b1]), self._p(d['grad_vertex_colors'][b0:b1]),
                     n, H, W, C, V, F, None, 0, 1, self._p(self.ws[i]), self.ws_bytes, stream)
                 _lib.check(rc, 'RasteriseGrad')
-                ev_run = torch.cuda.Event()
-                ev_run.record(self.s_run)
+                ev_bwd = torch.cuda.Event()
+                ev_bwd.record(self.s_run)
             with torch.cuda.stream(self.s_out):
-                self.s_out.wait_event(ev_run)
-                for k in ('pixels', 'grad_background'):
-                    self.h_out[k][b0:b1].copy_(d[k][b0:b1], non_blocking=True)
+                self.s_out.wait_event(ev_bwd)
+                self.h_out['grad_background'][b0:b1].copy_(d['grad_background'][b0:b1], non_blocking=True)
         with torch.cuda.stream(self.s_out):   # after the last chunk's kernels (already awaited on this stream)
             for k in ('grad_vertices', 'grad_vertex_colors'):
                 self.h_out[k].copy_(d[k], non_blocking=True)
