@@ -1006,8 +1006,13 @@ cudaError_t launch_backward(const float* vertices, const float* pixels, const fl
     float* const gc_out = grad_vertex_colors;
     if (padded) grad_vertex_colors = ws.gc_pad;
     const int gstride = padded ? 4 : d.C;
-    if ((e = cudaMemsetAsync(grad_vertices, 0, sizeof(float) * rows * 4, stream)) != cudaSuccess) return e;
-    if ((e = cudaMemsetAsync(grad_vertex_colors, 0, sizeof(float) * rows * gstride, stream)) != cudaSuccess) return e;
+    if (grad_vertex_colors == grad_vertices + rows * 4) {
+        // the two gradients are the halves of one flat buffer (what a multi-GPU job exchanges): one memset node
+        if ((e = cudaMemsetAsync(grad_vertices, 0, sizeof(float) * rows * (4 + gstride), stream)) != cudaSuccess) return e;
+    } else {
+        if ((e = cudaMemsetAsync(grad_vertices, 0, sizeof(float) * rows * 4, stream)) != cudaSuccess) return e;
+        if ((e = cudaMemsetAsync(grad_vertex_colors, 0, sizeof(float) * rows * gstride, stream)) != cudaSuccess) return e;
+    }
     const auto finish = [&]() -> cudaError_t {
         if (!padded) return cudaSuccess;
         const long long n = (long long)rows * 3;
