@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- fwd+bwd Mpixels/s of the rasterise hot path on BASELINE.json's workload.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg3|cfg4|cfg5|cfg2]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg3|cfg4|cfg5|cfg2|cube]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
 A "step" is one forward + one backward pass of the hot path over one batch of synthetic scenes
@@ -45,6 +45,7 @@ WORKLOADS = {
     'cfg4': ('config4', dict(batch=32, width=512, height=512), 'BASELINE cfg4 shard: batch=32/GPU, 512x512, 3-channel, icosphere-4'),
     'cfg5': ('config5', dict(batch=64, width=1024, height=1024), 'BASELINE cfg5: batch=64/GPU, 1024x1024, 3-channel, UV sphere (V=24866, F=49728)'),
     'cfg2': ('config2', dict(), 'BASELINE cfg2: batch=1, 256x256, 3-channel, icosphere-3'),
+    'cube': ('cube_batch', dict(batch=64, width=640, height=480), 'samples/simple.py cube, batch=64/GPU, 640x480, 3-channel, 12 triangles (large-face path)'),
 }
 
 
@@ -390,7 +391,11 @@ def check_against_oracle(prep, scene, images=1):
     sub = {k: np.ascontiguousarray(v[:n]) for k, v in scene.items()}
     pixels_o, ids_o = oracle.forward(**sub, return_face_ids=True)
     gp = prep.grad_pixels_host[:n]
-    gb_o, gv_o, gc_o = oracle.backward(sub['vertices'], sub['faces'], pixels_o, gp)
+    # RasteriseGrad is a function of (vertices, faces, pixels, grad_pixels): the oracle gets the SAME pixels the CUDA call
+    # gets (the benched forward's output, itself compared with the oracle's below).  Feeding each side its own pixels
+    # compares two different inputs wherever the Scharr norms tie -- flat-shaded faces (the cube) tie at most silhouette
+    # pixels, and the last bit of a pixel value then picks the dilation direction.
+    gb_o, gv_o, gc_o = oracle.backward(sub['vertices'], sub['faces'], np.ascontiguousarray(prep.pixels[:n].cpu().numpy()), gp)
 
     def worst(a, b):
         a = np.asarray(a, np.float64); b = np.asarray(b, np.float64)

@@ -221,6 +221,28 @@ def cube_scene(width=640, height=480):
     return _pack(np.zeros([1, height, width, 3]), clip[None], colours[None], f[None])
 
 
+def cube_batch(batch=64, width=640, height=480, seed=5):
+    """The lit cube of samples/simple.py at a different orientation per batch item: twelve triangles of tens of thousands
+    of pixels each -- the large-face path of the rasteriser (faces beyond SMALL_TILE_LIMIT tiles go to the per-image list)."""
+    rng = np.random.default_rng(seed)
+    v, f = cube()
+    v, f = split_vertices_by_face(v, f)
+    proj = perspective_projection(0.1, 20., 0.1, float(height) / width)
+    view = translation([0., -1.5, -3.5]) @ rodrigues([-0.3, 0., 0.])
+    clips, colours = [], []
+    for _ in range(batch):
+        world = _homogeneous(v) @ rodrigues([rng.uniform(-0.4, 0.4), rng.uniform(0., 2. * np.pi), 0.])
+        fn = np.cross(world[f[:, 1], :3] - world[f[:, 0], :3], world[f[:, 2], :3] - world[f[:, 0], :3])
+        fn /= (np.linalg.norm(fn, axis=1, keepdims=True) + 1e-12)
+        normals = np.zeros((v.shape[0], 3))
+        for k in range(3):
+            normals[f[:, k]] = fn
+        cosines = np.abs(normals @ -np.array([1., 0., 0.]))[:, None]
+        clips.append(world @ view @ proj)
+        colours.append(np.ones((v.shape[0], 3)) * cosines * 0.8 + 0.2)
+    return _pack(np.zeros([batch, height, width, 3]), np.stack(clips), np.stack(colours), np.repeat(f[None], batch, axis=0))
+
+
 # ---- BASELINE configurations -------------------------------------------------------------------------------
 
 def _posed_sphere_batch(verts, faces, batch, width, height, seed, ndc_radius=0.75, jitter=0.1):

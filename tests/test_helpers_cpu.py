@@ -283,3 +283,16 @@ def test_deferred_example_shades_an_oracle_gbuffer():
         spec = a * max(float((to_cam / np.linalg.norm(to_cam) + 1e-12) @ refl), 0.) ** 6.
         want = np.clip((diffuse + spec + 0.2 * a) * m + np.array([0., 0., 0.3]) * (1. - m), 0., 1.)
         np.testing.assert_allclose(img[r, c], want, atol=2e-5)
+
+
+def test_cube_batch_scene_is_the_sample_cube_at_other_orientations():
+    # the bench's large-face workload: same mesh, camera and shading as cube_scene (samples/simple.py:28-74)
+    from dirt_b200 import scenes
+    one, many = scenes.cube_scene(64, 48), scenes.cube_batch(batch=3, width=64, height=48, seed=2)
+    assert many['vertices'].shape == (3,) + one['vertices'].shape[1:] and many['faces'].shape == (3, 12, 3)
+    assert (many['faces'][0] == one['faces'][0]).all() and many['background'].shape == (3, 48, 64, 3)
+    assert not np.allclose(many['vertices'][0], many['vertices'][1])          # a pose per item
+    w = many['vertices'][..., 3]
+    assert (w > 0).all()                                                      # the whole cube in front of the camera
+    ndc = many['vertices'][..., :2] / w[..., None]
+    assert np.abs(ndc).max() < 1.0                                            # and inside the frame
