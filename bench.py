@@ -661,8 +661,11 @@ def run_ours(args):
 
     os.sched_setaffinity(0, full_affinity)   # the CPU legs below (oracle) use every host thread again
     checked = None
-    if args.check:
-        checked = check_against_oracle(prep, scene)
+    if args.check:   # default on; outside the timed region; never lets a checker problem take the bench line down
+        try:
+            checked = check_against_oracle(prep, scene)
+        except Exception as e:
+            checked = {'ok': False, 'error': '%s: %s' % (type(e).__name__, e)}
 
     peak, peak_src = measured_peak_gbs()
     fwd_bytes, bwd_bytes = algorithmic_bytes(B, H, W, C, V, F)
@@ -830,7 +833,9 @@ def main():
     ap.add_argument('--e2e-chunks', type=int, default=12, help='batch chunks of the host copy/compute pipeline')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-numpy-baseline', action='store_true', help='skip the numpy variants of the CPU baseline')
-    ap.add_argument('--check', action='store_true', help='after timing, validate the benched buffers against the CPU oracle ("checked": true)')
+    ap.add_argument('--check', dest='check', action='store_true', default=True,
+                    help='after timing, validate the benched buffers against the CPU oracle ("checked": true); on by default')
+    ap.add_argument('--no-check', dest='check', action='store_false', help='skip that validation')
     ap.add_argument('--no-numa-bind', action='store_true', help='do not pin the process to the NUMA node of its GPU')
     args = ap.parse_args()
     if args.impl == 'reference':
